@@ -1,0 +1,196 @@
+/*
+ * pb200.h -- C ABI of libpb200.so: the B200 (sm_100a) batch engine behind pyprobables'
+ * hash-then-scatter hot path.
+ *
+ * The reference (barrust/pyprobables v0.7.0, pure Python) has no FFI.  Each entry point below is
+ * what a ctypes binding for the cited reference method would call; the citing comments name the
+ * reference lines (relative to the reference repo root) whose per-key semantics the call
+ * reproduces for a whole batch.  INTEGRATION.md shows the reference-side ctypes stub.
+ *
+ * Conventions
+ *  - plain C types only; every function returns PB_OK (0) or a negative pb_status;
+ *    pb_last_error() returns a thread-local message for the last failure on this thread.
+ *  - handles are opaque; the library owns device memory, the caller owns every buffer it passes
+ *    and the library never keeps a caller pointer after the call returns.
+ *  - calls are synchronous on return (results visible to the host) unless the buffer arguments
+ *    are device pointers (on_device != 0), in which case work is only enqueued on the context's
+ *    stream: use pb_ctx_synchronize() or order your own work on pb_ctx_stream().
+ *  - a handle is not thread-safe; different handles may be driven from different host threads.
+ */
+#ifndef PB200_H
+#define PB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_VERSION 100 /* 0.1.0 */
+
+typedef enum pb_status {
+    PB_OK = 0,
+    PB_ERR_BAD_ARG = -1,
+    PB_ERR_CUDA = -2,
+    PB_ERR_OOM = -3,
+    PB_ERR_NO_DEVICE = -4,
+    PB_ERR_UNSUPPORTED = -5,
+    PB_ERR_CUCKOO_FULL = -6 /* cuckoo/cuckoo.py:515-516; see pb_cuckoo_add_keys */
+} pb_status;
+
+typedef struct pb_ctx pb_ctx;
+typedef struct pb_bloom pb_bloom;
+typedef struct pb_cms pb_cms;
+typedef struct pb_cuckoo pb_cuckoo;
+
+/* A batch of keys (KeyT = str | bytes, hashes.py:10).
+ *   data      packed symbols of all keys, back to back.
+ *   sym_width 1: one byte per symbol (bytes keys, ASCII/latin-1 str keys);
+ *             4: one little-endian u32 per symbol (str keys holding code points > 255:
+ *                hashes.py:98 hashes ord(c), not UTF-8 bytes).
+ *   offsets   NULL: every key is `stride` symbols long; else n+1 symbol offsets into data.
+ *   on_device 0: data/offsets are host pointers (pinned or pageable; copied in chunks, the copy
+ *                overlapped with the kernels); 1: device pointers on the context's device. */
+typedef struct pb_keys {
+    const void *data;
+    const uint64_t *offsets;
+    uint64_t n;
+    uint32_t stride;
+    uint32_t sym_width;
+    int32_t on_device;
+    int32_t reserved;
+} pb_keys;
+
+/* ---------------------------------------------------------------- library / context */
+int pb_version(void);
+const char *pb_last_error(void);
+int pb_device_count(int *out);
+/* stream: a cudaStream_t to run on (e.g. torch's), or NULL to let the context create its own. */
+int pb_ctx_create(int device, void *stream, pb_ctx **out);
+int pb_ctx_destroy(pb_ctx *ctx);
+int pb_ctx_synchronize(pb_ctx *ctx);
+int pb_ctx_stream(pb_ctx *ctx, void **out_stream);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int pb_ctx_launch_count(pb_ctx *ctx, uint64_t *out);
+/* tuning knobs: "bloom_insert_mode" (0 = auto, 1 = direct RED.OR, 2 = partition + L2-window apply),
+ * "bloom_window_log2_bits", "stage_bytes" (staging budget for partitioned insert),
+ * "h2d_chunk_keys" (host-buffer pipeline chunk). */
+int pb_ctx_set_option(pb_ctx *ctx, const char *name, int64_t value);
+int pb_ctx_get_option(pb_ctx *ctx, const char *name, int64_t *out);
+
+/* pinned host memory and raw device buffers, so a ctypes-only caller can stage inputs */
+int pb_host_alloc(size_t bytes, void **out);
+int pb_host_free(void *p);
+int pb_dev_alloc(pb_ctx *ctx, size_t bytes, void **out);
+int pb_dev_free(pb_ctx *ctx, void *p);
+int pb_memcpy_h2d(pb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int pb_memcpy_d2h(pb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int pb_memset_dev(pb_ctx *ctx, void *dst_dev, int value, size_t bytes);
+/* L2 flush helper for benchmarks: writes a scratch buffer larger than L2 */
+int pb_flush_l2(pb_ctx *ctx);
+
+/* ---------------------------------------------------------------- hashing (hashes.py:71-103) */
+/* default_fnv_1a(key, depth) for every key: out[i*depth + s] = fnv_1a(key_i, seed = s). */
+int pb_hash_keys(pb_ctx *ctx, const pb_keys *keys, uint32_t depth, uint64_t *out, int out_on_device);
+
+/* synthetic inputs of SURVEY.md 8(d) generated on the device (bench/test utility, not reference
+ * code): uniform key i = LE64(sm64(seed+2i)) || LE64(sm64(seed+2i+1)); rank key = LE64(r)||LE64(sm64(r)) */
+int pb_gen_uniform_keys(pb_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, void *out_dev);
+int pb_gen_rank_keys(pb_ctx *ctx, const uint64_t *ranks_dev, uint64_t n, void *out_dev);
+
+/* ---------------------------------------------------------------- Bloom (blooms/bloom.py) */
+/* state = ceil(num_bits/8) bytes, bit b lives in byte b/8 at mask 1<<(b%8) (bloom.py:247-249).
+ * num_bits / k come from the Python side (bloom.py:463-483 stays host float math). */
+int pb_bloom_create(pb_ctx *ctx, uint64_t num_bits, uint32_t k, pb_bloom **out);
+int pb_bloom_destroy(pb_bloom *b);
+int pb_bloom_clear(pb_bloom *b);                                         /* bloom.py:217-221 */
+int pb_bloom_upload(pb_bloom *b, const uint8_t *bytes, uint64_t nbytes); /* bloom.py:548 */
+int pb_bloom_download(pb_bloom *b, uint8_t *bytes, uint64_t nbytes);     /* bloom.py:299 */
+int pb_bloom_device_ptr(pb_bloom *b, void **out_dev, uint64_t *out_nbytes);
+/* BloomFilter.add for every key (bloom.py:234-250, hashes via hashes.py:71-103) */
+int pb_bloom_add_keys(pb_bloom *b, const pb_keys *keys);
+/* BloomFilter.check for every key (bloom.py:252-272): out[i] = 1/0 */
+int pb_bloom_check_keys(pb_bloom *b, const pb_keys *keys, uint8_t *out, int out_on_device);
+/* BloomFilter.add_alt / check_alt (bloom.py:241-250, :261-272) with caller-made hashes,
+ * hashes[i*k + s] (a custom hash_function ran on the host); reduced % num_bits on the device. */
+int pb_bloom_add_hashes(pb_bloom *b, const uint64_t *hashes, uint64_t n, int on_device);
+int pb_bloom_check_hashes(pb_bloom *b, const uint64_t *hashes, uint64_t n, int on_device, uint8_t *out,
+                          int out_on_device);
+int pb_bloom_popcount(pb_bloom *b, uint64_t *out); /* bloom.py:552-557 */
+/* multi-GPU range sharding: this handle owns bits [lo, hi) of a num_bits-bit filter.
+ * Keys are hashed against the GLOBAL num_bits; only indices inside [lo, hi) touch this shard. */
+int pb_bloom_create_shard(pb_ctx *ctx, uint64_t num_bits, uint32_t k, uint64_t lo_bit, uint64_t hi_bit,
+                          pb_bloom **out);
+/* route: hash keys -> global bit index -> owner = idx / shard_bits; writes each owner's indices
+ * (u64, global) contiguously into out_idx at out_offsets[owner]; counts[owner] returned.
+ * All buffers are device pointers (they feed an NCCL all-to-all). */
+int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint64_t shard_bits,
+                        uint32_t n_shards, uint64_t *out_idx_dev, uint64_t slot_cap, uint64_t *counts_dev);
+/* apply global bit indices that fall into this shard's [lo, hi) (others are an error count) */
+int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n);
+int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, uint8_t *out_dev);
+
+/* ---------------------------------------------------------------- Count-Min (countminsketch.py) */
+/* state = int32[depth][width] row-major; bin of row i = (h_i % width) + i*width (:275). */
+int pb_cms_create(pb_ctx *ctx, uint32_t width, uint32_t depth, pb_cms **out);
+int pb_cms_destroy(pb_cms *c);
+int pb_cms_clear(pb_cms *c); /* :240-244 */
+int pb_cms_upload(pb_cms *c, const int32_t *bins, uint64_t count);
+int pb_cms_download(pb_cms *c, int32_t *bins, uint64_t count);
+int pb_cms_device_ptr(pb_cms *c, void **out_dev, uint64_t *out_count);
+/* CountMinSketch.add for every key (:257-288): bins saturate at INT32_MAX (:280-282);
+ * num_els == NULL -> every key adds scalar_num_els.  *elements_added is updated with the
+ * saturating sum (:285-287).  num_els follows keys->on_device. */
+int pb_cms_add_keys(pb_cms *c, const pb_keys *keys, const int64_t *num_els, int64_t scalar_num_els,
+                    int64_t *elements_added_inout);
+/* CountMinSketch.check (:323-340) with query_type 0 = min (:430-432), 1 = mean (:434-436),
+ * 2 = mean-min (:438-453; needs elements_added). */
+int pb_cms_check_keys(pb_cms *c, const pb_keys *keys, int query_type, int64_t elements_added, int64_t *out,
+                      int out_on_device);
+/* add_alt / check_alt (:267-288, :332-340) with caller-made hashes[i*depth + r] */
+int pb_cms_add_hashes(pb_cms *c, const uint64_t *hashes, uint64_t n, int on_device, const int64_t *num_els,
+                      int64_t scalar_num_els, int64_t *elements_added_inout);
+int pb_cms_check_hashes(pb_cms *c, const uint64_t *hashes, uint64_t n, int on_device, int query_type,
+                        int64_t elements_added, int64_t *out, int out_on_device);
+/* CountMinSketch.join (:380-391) against a second table already on this device (multi-GPU merge) */
+int pb_cms_join_buffer(pb_cms *c, const int32_t *other_dev, uint64_t count);
+
+/* ---------------------------------------------------------------- Cuckoo (cuckoo/cuckoo.py) */
+/* state = u32[capacity][bucket_size], 0 = empty slot; fingerprint 0 (legal, utilities.py:35) is
+ * kept as a side flag because it is indistinguishable from "empty" in the reference's own export
+ * format (cuckoo.py:346, :429).  fp = low fp_bits of fnv_1a(key) (:499-500);
+ * idx_1 = fp % capacity; idx_2 = fnv_1a(str(fp)) % capacity (:488-489). */
+int pb_cuckoo_create(pb_ctx *ctx, uint64_t capacity, uint32_t bucket_size, uint32_t max_swaps, uint32_t fp_bits,
+                     uint64_t rng_seed, pb_cuckoo **out);
+int pb_cuckoo_destroy(pb_cuckoo *c);
+int pb_cuckoo_clear(pb_cuckoo *c);
+/* CuckooFilter.add for every key (:291-304): fingerprints already present are skipped (:300-302),
+ * the rest are placed (idx_1, then idx_2, then an eviction walk of <= max_swaps, :361-392).
+ * *n_added = fingerprints newly stored (what elements_added grows by).  Fingerprints left homeless
+ * after max_swaps are returned in failed_fps (up to failed_cap) with *n_failed their total count
+ * and the call returns PB_ERR_CUCKOO_FULL so the caller can expand or raise (:508-516). */
+int pb_cuckoo_add_keys(pb_cuckoo *c, const pb_keys *keys, uint64_t *n_added, uint64_t *n_failed,
+                       uint32_t *failed_fps, uint64_t failed_cap);
+/* same, starting from fingerprints (used by expand, :467-481) */
+int pb_cuckoo_add_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, int on_device, uint64_t *n_added,
+                               uint64_t *n_failed, uint32_t *failed_fps, uint64_t failed_cap);
+/* CuckooFilter.check (:306-315) */
+int pb_cuckoo_check_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device);
+/* _generate_fingerprint_info (:492-506): per key fp, idx_1, idx_2 */
+int pb_cuckoo_fingerprint_info(pb_cuckoo *c, const pb_keys *keys, uint32_t *fp, uint64_t *idx1, uint64_t *idx2,
+                               int out_on_device);
+int pb_cuckoo_count(pb_cuckoo *c, uint64_t *out); /* stored fingerprints incl. the fp-0 flag */
+int pb_cuckoo_download(pb_cuckoo *c, uint32_t *slots, uint64_t count, int *has_zero_fp); /* :340-347 */
+int pb_cuckoo_upload(pb_cuckoo *c, const uint32_t *slots, uint64_t count, int has_zero_fp);
+
+/* ---------------------------------------------------------------- roofline micro-benchmarks */
+/* n random RED.OR.b32 / atomicAdd.s32 over `words` 32-bit words with pre-generated uniform
+ * indices and no hashing: the empirical random-atomic ceiling SURVEY 8(d) asks for. ms = device time. */
+int pb_microbench_random_atomic(pb_ctx *ctx, uint64_t words, uint64_t n, int op /*0=or,1=add*/, int reps,
+                                float *ms_best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB200_H */
