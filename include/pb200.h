@@ -73,9 +73,14 @@ int pb_ctx_synchronize(pb_ctx *ctx);
 int pb_ctx_stream(pb_ctx *ctx, void **out_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int pb_ctx_launch_count(pb_ctx *ctx, uint64_t *out);
+/* Device time per kernel name for the launches made since the previous call, while the "kernel_timing"
+ * option is 1: text lines "name launches total_ms\n" (CUDA events on the context's stream). */
+int pb_ctx_kernel_times(pb_ctx *ctx, char *buf, size_t cap);
 /* tuning knobs: "bloom_insert_mode" (0 = auto, 1 = direct RED.OR, 2 = partition + L2-window apply),
  * "bloom_window_log2_bits", "stage_bytes" (staging budget for partitioned insert),
- * "h2d_chunk_keys" (host-buffer pipeline chunk). */
+ * "h2d_chunk_keys" (host-buffer pipeline chunk), "cms_aggregate" (warp-combine equal keys, default 1),
+ * "cuckoo_serial" (1 = one-thread in-order cuckoo insert that reproduces the reference's append order),
+ * "kernel_timing" (1 = bracket hot kernels with events, see pb_ctx_kernel_times). */
 int pb_ctx_set_option(pb_ctx *ctx, const char *name, int64_t value);
 int pb_ctx_get_option(pb_ctx *ctx, const char *name, int64_t *out);
 
@@ -177,17 +182,27 @@ int pb_cuckoo_add_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, in
                                uint64_t *n_failed, uint32_t *failed_fps, uint64_t failed_cap);
 /* CuckooFilter.check (:306-315) */
 int pb_cuckoo_check_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device);
+/* _check_if_present (:440-446) from fingerprints (custom hash_function ran on the host) */
+int pb_cuckoo_check_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, int on_device, uint8_t *out,
+                                 int out_on_device);
 /* _generate_fingerprint_info (:492-506): per key fp, idx_1, idx_2 */
 int pb_cuckoo_fingerprint_info(pb_cuckoo *c, const pb_keys *keys, uint32_t *fp, uint64_t *idx1, uint64_t *idx2,
                                int out_on_device);
 int pb_cuckoo_count(pb_cuckoo *c, uint64_t *out); /* stored fingerprints incl. the fp-0 flag */
 int pb_cuckoo_download(pb_cuckoo *c, uint32_t *slots, uint64_t count, int *has_zero_fp); /* :340-347 */
 int pb_cuckoo_upload(pb_cuckoo *c, const uint32_t *slots, uint64_t count, int has_zero_fp);
+int pb_cuckoo_device_ptr(pb_cuckoo *c, void **out_dev, uint64_t *out_count);
+int pb_cuckoo_capacity(pb_cuckoo *c, uint64_t *out);
+/* _expand_logic (:455-481): the table becomes new_capacity buckets and every stored fingerprint is
+ * re-inserted on the device.  Fingerprints that find no home are returned like pb_cuckoo_add_keys does
+ * (PB_ERR_CUCKOO_FULL; the reference raises "The CuckooFilter failed to expand", :463-465). */
+int pb_cuckoo_expand(pb_cuckoo *c, uint64_t new_capacity, uint64_t *n_failed, uint32_t *failed_fps, uint64_t failed_cap);
 
 /* ---------------------------------------------------------------- roofline micro-benchmarks */
 /* n random RED.OR.b32 / atomicAdd.s32 over `words` 32-bit words with pre-generated uniform
  * indices and no hashing: the empirical random-atomic ceiling SURVEY 8(d) asks for. ms = device time. */
-int pb_microbench_random_atomic(pb_ctx *ctx, uint64_t words, uint64_t n, int op /*0=or,1=add*/, int reps,
+int pb_microbench_random_atomic(pb_ctx *ctx, uint64_t words, uint64_t n,
+                                int op /*0=RED.OR 1=RED.ADD 2=random 32-bit load 3=streaming copy of `words`*/, int reps,
                                 float *ms_best);
 
 #ifdef __cplusplus

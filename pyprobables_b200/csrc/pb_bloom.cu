@@ -1,0 +1,733 @@
+// pb_bloom.cu -- BloomFilter.add / check for whole batches (reference: probables/blooms/bloom.py:234-272).
+//
+// State: the reference's byte array (bit b -> byte b/8, mask 1<<(b%8), bloom.py:247-249) held as
+// little-endian u32 words, so bit b is bit (b & 31) of word (b >> 5) and RED.OR.b32 reproduces the
+// byte array exactly.
+//
+// Insert has two device paths:
+//   direct      one thread per key: k FNV chains -> exact % num_bits -> k RED.OR.b32 into HBM.
+//               Every RED is a random 32-byte sector read-modify-write (64 B of DRAM traffic).
+//   partitioned pass 1 hashes the keys once and bins the bit indices by bitmap *window*
+//               (2^W bits, sized to sit in B200's 126 MB L2) into a staging area with coalesced,
+//               write-combined stores; pass 2 walks the windows in order and applies each
+//               window's indices with RED.OR while that window is L2-resident.  DRAM traffic drops
+//               from 16+64k to about 16+8k bytes per key plus one read+write of the bitmap per chunk.
+// Bucket overflow (skewed / duplicate keys) falls back to direct REDs, so the result is exact for
+// any input.
+#include <algorithm>
+#include <new>
+
+#include "pb_common.cuh"
+#include "pb_hash.cuh"
+#include "pb_keys.cuh"
+
+using namespace pb;
+
+struct pb_bloom {
+    pb_ctx *ctx = nullptr;
+    uint64_t num_bits = 0;  // modulus of the (global) filter
+    uint32_t k = 0;
+    uint64_t lo_bit = 0, hi_bit = 0;  // bits owned by this handle ([0, num_bits) unless sharded)
+    uint32_t *words = nullptr;
+    uint64_t nbytes = 0;  // ceil((hi-lo)/8)
+    uint64_t nwords = 0;  // allocation, multiple of 4 words
+    FastMod fm;
+};
+
+namespace pb {
+
+struct BloomDev {
+    uint32_t *words;
+    FastMod fm;
+    uint64_t lo, hi;  // owned bit range
+    uint32_t k;
+};
+
+__device__ __forceinline__ void bloom_set(const BloomDev &b, uint64_t h) {
+    const uint64_t idx = fastmod(h, b.fm);
+    if (idx >= b.lo && idx < b.hi) {
+        const uint64_t l = idx - b.lo;
+        atomicOr(b.words + (l >> 5), 1u << (uint32_t)(l & 31));  // result unused -> RED.E.OR
+    }
+}
+
+__device__ __forceinline__ uint32_t bloom_test(const BloomDev &b, uint64_t h) {
+    const uint64_t idx = fastmod(h, b.fm);
+    if (idx >= b.lo && idx < b.hi) {
+        const uint64_t l = idx - b.lo;
+        return (__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u;
+    }
+    return 1u;  // not this shard's bit: neutral for the AND
+}
+
+// ---------------------------------------------------------------- direct insert / check
+template <int KG>
+__global__ void __launch_bounds__(256) bloom_add_fixed16(const uint4 *__restrict__ keys, uint64_t n, BloomDev b) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 w = __ldcs(keys + i);
+        for (uint32_t s0 = 0; s0 < b.k; s0 += KG) {
+            uint64_t h[KG];
+            fnv_group_16<KG>(w, s0, h);
+#pragma unroll
+            for (int j = 0; j < KG; ++j)
+                if (s0 + j < b.k) bloom_set(b, h[j]);
+        }
+    }
+}
+
+template <int KG>
+__global__ void __launch_bounds__(256)
+    bloom_check_fixed16(const uint4 *__restrict__ keys, uint64_t n, BloomDev b, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 w = __ldcs(keys + i);
+        uint32_t ok = 1u;
+        for (uint32_t s0 = 0; s0 < b.k; s0 += KG) {
+            uint64_t h[KG];
+            fnv_group_16<KG>(w, s0, h);
+            uint32_t bit[KG];
+            // issue all probes of the group before combining them: k independent sector reads in flight
+#pragma unroll
+            for (int j = 0; j < KG; ++j) bit[j] = (s0 + j < b.k) ? bloom_test(b, h[j]) : 1u;
+#pragma unroll
+            for (int j = 0; j < KG; ++j) ok &= bit[j];
+        }
+        out[i] = (uint8_t)ok;
+    }
+}
+
+template <int KG, int SYMW, bool CHECK>
+__global__ void __launch_bounds__(kTileKeys) bloom_staged(DevKeys dk, BloomDev b, uint8_t *__restrict__ out) {
+    __shared__ TileSmem sm;
+    if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t first = tile * kTileKeys;
+        const uint32_t count = (uint32_t)min((uint64_t)kTileKeys, dk.n - first);
+        const KeyRef kr = stage_tile<SYMW>(dk, first, count, sm, parity);
+        if (threadIdx.x < count) {
+            uint32_t ok = 1u;
+            for (uint32_t s0 = 0; s0 < b.k; s0 += KG) {
+                uint64_t h[KG];
+                fnv_group_ptr<KG, SYMW>(kr.p, kr.len, s0, h);
+#pragma unroll
+                for (int j = 0; j < KG; ++j) {
+                    if (s0 + j < b.k) {
+                        if (CHECK) ok &= bloom_test(b, h[j]);
+                        else bloom_set(b, h[j]);
+                    }
+                }
+            }
+            if (CHECK) out[first + threadIdx.x] = (uint8_t)ok;
+        }
+    }
+}
+
+// add_alt / check_alt: hashes made by a host-side hash_function (bloom.py:241-250, :261-272)
+__global__ void __launch_bounds__(256) bloom_add_hashes_kernel(const uint64_t *__restrict__ h, uint64_t total, BloomDev b) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        bloom_set(b, h[i]);
+}
+__global__ void __launch_bounds__(256)
+    bloom_check_hashes_kernel(const uint64_t *__restrict__ h, uint64_t n, BloomDev b, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t ok = 1u;
+        for (uint32_t s = 0; s < b.k; ++s) ok &= bloom_test(b, h[i * b.k + s]);
+        out[i] = (uint8_t)ok;
+    }
+}
+
+// bit indices that already went through % num_bits (multi-GPU apply side)
+__global__ void __launch_bounds__(256)
+    bloom_add_idx_kernel(const uint64_t *__restrict__ idx, uint64_t n, BloomDev b, unsigned long long *stray) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = __ldcs(idx + i);
+        if (g >= b.lo && g < b.hi) {
+            const uint64_t l = g - b.lo;
+            atomicOr(b.words + (l >> 5), 1u << (uint32_t)(l & 31));
+        } else {
+            atomicAdd(stray, 1ull);
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+    bloom_test_idx_kernel(const uint64_t *__restrict__ idx, uint64_t n, BloomDev b, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = __ldcs(idx + i);
+        uint32_t bit = 0;
+        if (g >= b.lo && g < b.hi) {
+            const uint64_t l = g - b.lo;
+            bit = (__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u;
+        }
+        out[i] = (uint8_t)bit;
+    }
+}
+
+// bloom.py:552-557
+__global__ void __launch_bounds__(256) popcount_kernel(const uint4 *__restrict__ w, uint64_t n4, unsigned long long *out) {
+    unsigned long long c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(w + i);
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// ---------------------------------------------------------------- partitioned insert
+constexpr int kMaxWindows = 1024;
+
+struct PartDev {
+    uint32_t *stage;              // n_windows * cap local indices
+    unsigned long long *cursors;  // n_windows
+    uint64_t cap;                 // per-window capacity (items, multiple of 4)
+    uint32_t window_log2;         // bits per window = 1 << window_log2 (<= 32)
+    uint32_t n_windows;
+};
+
+// pass 1: hash, bin by window, write window-local bit indices
+template <int KG, int NG>
+__global__ void __launch_bounds__(256) bloom_part_fixed16(const uint4 *__restrict__ keys, uint64_t n, BloomDev b, PartDev p) {
+    __shared__ uint32_t hist[kMaxWindows];
+    __shared__ unsigned long long base[kMaxWindows];
+    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t local_mask = p.window_log2 >= 32 ? 0xFFFFFFFFu : ((1u << p.window_log2) - 1u);
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (uint32_t w = threadIdx.x; w < p.n_windows; w += blockDim.x) hist[w] = 0;
+        __syncthreads();
+        const uint64_t i = tile * blockDim.x + threadIdx.x;
+        uint64_t idx[NG][KG];
+        uint32_t rank[NG][KG];
+        if (i < n) {
+            const uint4 w = __ldcs(keys + i);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                uint64_t h[KG];
+                fnv_group_16<KG>(w, g * KG, h);
+#pragma unroll
+                for (int j = 0; j < KG; ++j) {
+                    if ((uint32_t)(g * KG + j) < b.k) {
+                        idx[g][j] = fastmod(h[j], b.fm);
+                        rank[g][j] = atomicAdd(&hist[(uint32_t)(idx[g][j] >> p.window_log2)], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < p.n_windows; w += blockDim.x)
+            base[w] = hist[w] ? atomicAdd(p.cursors + w, (unsigned long long)hist[w]) : 0ull;
+        __syncthreads();
+        if (i < n) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+#pragma unroll
+                for (int j = 0; j < KG; ++j) {
+                    if ((uint32_t)(g * KG + j) < b.k) {
+                        const uint32_t w = (uint32_t)(idx[g][j] >> p.window_log2);
+                        const unsigned long long pos = base[w] + rank[g][j];
+                        if (pos < p.cap) {
+                            __stcs(p.stage + (uint64_t)w * p.cap + pos, (uint32_t)idx[g][j] & local_mask);
+                        } else {  // window overflow (skewed keys): apply straight to the bitmap
+                            atomicOr(b.words + (idx[g][j] >> 5), 1u << (uint32_t)(idx[g][j] & 31));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2: windows in launch order; each window's bitmap slice stays in L2 while its list streams by
+__global__ void __launch_bounds__(256) bloom_apply_windows(BloomDev b, PartDev p, uint32_t ctas_per_window) {
+    const uint32_t w = blockIdx.x / ctas_per_window;
+    const uint32_t c = blockIdx.x % ctas_per_window;
+    unsigned long long cnt = p.cursors[w];
+    if (cnt > p.cap) cnt = p.cap;
+    uint32_t *words = b.words + ((uint64_t)w << (p.window_log2 - 5));
+    const uint32_t *list = p.stage + (uint64_t)w * p.cap;
+    const uint64_t n4 = cnt >> 2;
+    const uint4 *list4 = reinterpret_cast<const uint4 *>(list);
+    for (uint64_t i = (uint64_t)c * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)ctas_per_window * blockDim.x) {
+        const uint4 v = __ldcs(list4 + i);
+        atomicOr(words + (v.x >> 5), 1u << (v.x & 31));
+        atomicOr(words + (v.y >> 5), 1u << (v.y & 31));
+        atomicOr(words + (v.z >> 5), 1u << (v.z & 31));
+        atomicOr(words + (v.w >> 5), 1u << (v.w & 31));
+    }
+    if (c == 0) {
+        for (uint64_t i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t v = list[i];
+            atomicOr(words + (v >> 5), 1u << (v & 31));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- multi-GPU routing
+// hash keys, find the owning shard of every bit index, append the (global) index to that shard's slot.
+template <int KG>
+__global__ void __launch_bounds__(256) bloom_route_fixed16(const uint4 *__restrict__ keys, uint64_t n, FastMod fm, uint32_t k,
+                                                           FastMod shard_div, uint64_t shard_bits, uint32_t n_shards,
+                                                           uint64_t *__restrict__ out, uint64_t slot_cap,
+                                                           unsigned long long *counts) {
+    __shared__ uint32_t hist[64];
+    __shared__ unsigned long long base[64];
+    (void)shard_bits;
+    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        if (threadIdx.x < n_shards) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t i = tile * blockDim.x + threadIdx.x;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (i < n) w = __ldcs(keys + i);
+        for (uint32_t s0 = 0; s0 < k; s0 += KG) {
+            uint64_t h[KG];
+            uint64_t idx[KG];
+            uint32_t dst[KG], rank[KG];
+            fnv_group_16<KG>(w, s0, h);
+#pragma unroll
+            for (int j = 0; j < KG; ++j) {
+                if (i < n && s0 + j < k) {
+                    idx[j] = fastmod(h[j], fm);
+                    dst[j] = (uint32_t)fastdiv(idx[j], shard_div);
+                    rank[j] = atomicAdd(&hist[dst[j]], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < n_shards) {
+                base[threadIdx.x] =
+                    hist[threadIdx.x] ? atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]) : 0ull;
+                hist[threadIdx.x] = 0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < KG; ++j) {
+                if (i < n && s0 + j < k) {
+                    const unsigned long long pos = base[dst[j]] + rank[j];
+                    if (pos < slot_cap) out[(uint64_t)dst[j] * slot_cap + pos] = idx[j];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static BloomDev dev_view(const pb_bloom *b) {
+    BloomDev d;
+    d.words = b->words;
+    d.fm = b->fm;
+    d.lo = b->lo_bit;
+    d.hi = b->hi_bit;
+    d.k = b->k;
+    return d;
+}
+
+template <int KG>
+static int launch_add_direct(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd) {
+    launch_begin(ctx);
+    if (is_fixed16(dk)) {
+        bloom_add_fixed16<KG><<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, bd);
+    } else {
+        uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+        int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+        if (dk.sym_width == 4) bloom_staged<KG, 4, false><<<grid, kTileKeys, 0, ctx->stream>>>(dk, bd, nullptr);
+        else bloom_staged<KG, 1, false><<<grid, kTileKeys, 0, ctx->stream>>>(dk, bd, nullptr);
+    }
+    return check_launch(ctx, "bloom_add");
+}
+
+template <int KG>
+static int launch_check(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd, uint8_t *out) {
+    launch_begin(ctx);
+    if (is_fixed16(dk)) {
+        bloom_check_fixed16<KG><<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, bd, out);
+    } else {
+        uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+        int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+        if (dk.sym_width == 4) bloom_staged<KG, 4, true><<<grid, kTileKeys, 0, ctx->stream>>>(dk, bd, out);
+        else bloom_staged<KG, 1, true><<<grid, kTileKeys, 0, ctx->stream>>>(dk, bd, out);
+    }
+    return check_launch(ctx, "bloom_check");
+}
+
+#define PB_DISPATCH_KG(kg, CALL)            \
+    switch (kg) {                           \
+        case 1: st = CALL(1); break;        \
+        case 2: st = CALL(2); break;        \
+        case 3: st = CALL(3); break;        \
+        case 4: st = CALL(4); break;        \
+        case 5: st = CALL(5); break;        \
+        case 6: st = CALL(6); break;        \
+        case 7: st = CALL(7); break;        \
+        default: st = CALL(8); break;       \
+    }
+
+struct PartPlan {
+    bool use = false;
+    uint32_t window_log2 = 0;
+    uint32_t n_windows = 0;
+    uint64_t cap = 0;
+    uint64_t chunk_keys = 0;
+    int kg = 0, ng = 0;
+};
+
+// Decide whether (and how) a batch of n keys goes through the partitioned path.
+static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
+    PartPlan pl;
+    pb_ctx *ctx = b->ctx;
+    const int64_t mode = ctx->bloom_insert_mode;
+    if (mode == 1 || !fixed16 || b->k > 16) return pl;
+    if (b->lo_bit != 0 || b->hi_bit != b->num_bits) return pl;  // shards take routed indices instead
+    const uint64_t l2 = ctx->l2_bytes ? ctx->l2_bytes : ((uint64_t)96 << 20);
+    if (mode == 0) {
+        // auto: only when the bitmap cannot live in L2 and the batch is large enough to amortise
+        // one extra read+write of the bitmap
+        if (b->nbytes <= l2) return pl;
+        if ((double)n * b->k * 64.0 < 4.0 * (double)b->nbytes) return pl;
+    }
+    uint32_t wl = (uint32_t)ctx->bloom_window_log2_bits;
+    if (wl > 32) wl = 32;
+    while (((b->num_bits + ((1ull << wl) - 1)) >> wl) > (uint64_t)kMaxWindows && wl < 32) ++wl;
+    const uint64_t nw = (b->num_bits + ((1ull << wl) - 1)) >> wl;
+    if (nw > (uint64_t)kMaxWindows || wl < 5) return pl;
+    uint64_t stage_items = (uint64_t)ctx->stage_bytes / 4;
+    uint64_t cap = (stage_items / nw) & ~(uint64_t)3;
+    const double per_key_per_window = (double)b->k * (double)(1ull << wl) / (double)b->num_bits;  // <= k
+    // shrink the staging to what this batch needs
+    uint64_t need = (uint64_t)((double)n * std::min(per_key_per_window, (double)b->k) * 1.03) + 8192;
+    need = (need + 3) & ~(uint64_t)3;
+    if (need < cap) cap = need;
+    if (cap < 16384) return pl;
+    uint64_t chunk = (uint64_t)(((double)cap - 8192.0) / 1.03 / std::min(per_key_per_window, (double)b->k));
+    if (chunk < 1024) return pl;
+    pl.use = true;
+    pl.window_log2 = wl;
+    pl.n_windows = (uint32_t)nw;
+    pl.cap = cap;
+    pl.chunk_keys = chunk;
+    if (b->k <= 8) {
+        pl.kg = (int)b->k;
+        pl.ng = 1;
+    } else {
+        pl.kg = (int)((b->k + 1) / 2);
+        pl.ng = 2;
+    }
+    return pl;
+}
+
+template <int KG, int NG>
+static int launch_part(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd, const PartDev &pd) {
+    launch_begin(ctx);
+    bloom_part_fixed16<KG, NG><<<grid_for(ctx, dk.n, 256, 6), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, bd, pd);
+    return check_launch(ctx, "bloom_part");
+}
+
+struct AddArgs {
+    pb_bloom *b;
+    PartPlan plan;
+};
+
+static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    (void)first;
+    (void)slot;
+    AddArgs *a = (AddArgs *)user;
+    pb_bloom *b = a->b;
+    const BloomDev bd = dev_view(b);
+    int st = PB_OK;
+    if (a->plan.use && is_fixed16(dk)) {
+        const PartPlan &pl = a->plan;
+        PB_TRY(scratch_reserve(ctx, ctx->part_stage, (size_t)pl.n_windows * pl.cap * 4));
+        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, (size_t)kMaxWindows * 8));
+        PartDev pd;
+        pd.stage = (uint32_t *)ctx->part_stage.p;
+        pd.cursors = (unsigned long long *)ctx->part_cursors.p;
+        pd.cap = pl.cap;
+        pd.window_log2 = pl.window_log2;
+        pd.n_windows = pl.n_windows;
+        PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 8, ctx->stream));
+        const int code = pl.ng * 100 + pl.kg;
+        switch (code) {
+            case 101: st = launch_part<1, 1>(ctx, dk, bd, pd); break;
+            case 102: st = launch_part<2, 1>(ctx, dk, bd, pd); break;
+            case 103: st = launch_part<3, 1>(ctx, dk, bd, pd); break;
+            case 104: st = launch_part<4, 1>(ctx, dk, bd, pd); break;
+            case 105: st = launch_part<5, 1>(ctx, dk, bd, pd); break;
+            case 106: st = launch_part<6, 1>(ctx, dk, bd, pd); break;
+            case 107: st = launch_part<7, 1>(ctx, dk, bd, pd); break;
+            case 108: st = launch_part<8, 1>(ctx, dk, bd, pd); break;
+            case 205: st = launch_part<5, 2>(ctx, dk, bd, pd); break;
+            case 206: st = launch_part<6, 2>(ctx, dk, bd, pd); break;
+            case 207: st = launch_part<7, 2>(ctx, dk, bd, pd); break;
+            case 208: st = launch_part<8, 2>(ctx, dk, bd, pd); break;
+            default:
+                set_error("internal: no partition kernel for k=%u", b->k);
+                return PB_ERR_UNSUPPORTED;
+        }
+        PB_TRY(st);
+        const uint32_t cpw = (uint32_t)ctx->num_sms * 2;
+        launch_begin(ctx);
+        bloom_apply_windows<<<pl.n_windows * cpw, 256, 0, ctx->stream>>>(bd, pd, cpw);
+        return check_launch(ctx, "bloom_apply_windows");
+    }
+    const int kg = pick_group(b->k);
+#define CALL(K) launch_add_direct<K>(ctx, dk, bd)
+    PB_DISPATCH_KG(kg, CALL)
+#undef CALL
+    return st;
+}
+
+struct CheckArgs {
+    pb_bloom *b;
+    uint8_t *out_dev;
+    uint8_t *out_host;
+};
+
+static int check_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    CheckArgs *a = (CheckArgs *)user;
+    const BloomDev bd = dev_view(a->b);
+    uint8_t *out = a->out_dev ? a->out_dev + first : nullptr;
+    if (!out) {
+        PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n));
+        out = (uint8_t *)ctx->out_stage[slot].p;
+    }
+    int st = PB_OK;
+    const int kg = pick_group(a->b->k);
+#define CALL(K) launch_check<K>(ctx, dk, bd, out)
+    PB_DISPATCH_KG(kg, CALL)
+#undef CALL
+    PB_TRY(st);
+    if (a->out_host) PB_CUDA(cudaMemcpyAsync(a->out_host + first, out, dk.n, cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
+static int bloom_alloc(pb_ctx *ctx, uint64_t num_bits, uint32_t k, uint64_t lo, uint64_t hi, pb_bloom **out) {
+    PB_REQUIRE(ctx && out, "NULL argument");
+    PB_REQUIRE(num_bits >= 1, "num_bits must be >= 1");
+    PB_REQUIRE(k >= 1, "number of hashes must be >= 1");
+    PB_REQUIRE(lo < hi && hi <= num_bits, "bad shard range");
+    PB_REQUIRE((lo & 31u) == 0, "shard start must be a multiple of 32 bits");
+    DeviceGuard g(ctx->device);
+    pb_bloom *b = new (std::nothrow) pb_bloom();
+    if (!b) return PB_ERR_OOM;
+    b->ctx = ctx;
+    b->num_bits = num_bits;
+    b->k = k;
+    b->lo_bit = lo;
+    b->hi_bit = hi;
+    b->nbytes = (hi - lo + 7) / 8;
+    b->nwords = (((b->nbytes + 3) / 4) + 3) & ~(uint64_t)3;
+    b->fm = make_fastmod(num_bits);
+    cudaError_t e = cudaMalloc(&b->words, b->nwords * 4);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %llu bitmap bytes failed: %s", (unsigned long long)(b->nwords * 4), cudaGetErrorString(e));
+        delete b;
+        return PB_ERR_OOM;
+    }
+    e = cudaMemsetAsync(b->words, 0, b->nwords * 4, ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("memset failed: %s", cudaGetErrorString(e));
+        cudaFree(b->words);
+        delete b;
+        return PB_ERR_CUDA;
+    }
+    *out = b;
+    return PB_OK;
+}
+
+}  // namespace pb
+
+extern "C" {
+
+int pb_bloom_create(pb_ctx *ctx, uint64_t num_bits, uint32_t k, pb_bloom **out) {
+    return bloom_alloc(ctx, num_bits, k, 0, num_bits, out);
+}
+
+int pb_bloom_create_shard(pb_ctx *ctx, uint64_t num_bits, uint32_t k, uint64_t lo_bit, uint64_t hi_bit, pb_bloom **out) {
+    return bloom_alloc(ctx, num_bits, k, lo_bit, hi_bit, out);
+}
+
+int pb_bloom_destroy(pb_bloom *b) {
+    if (!b) return PB_OK;
+    DeviceGuard g(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->words);
+    delete b;
+    return PB_OK;
+}
+
+int pb_bloom_clear(pb_bloom *b) {
+    PB_REQUIRE(b, "handle is NULL");
+    DeviceGuard g(b->ctx->device);
+    PB_CUDA(cudaMemsetAsync(b->words, 0, b->nwords * 4, b->ctx->stream));
+    return PB_OK;
+}
+
+int pb_bloom_upload(pb_bloom *b, const uint8_t *bytes, uint64_t nbytes) {
+    PB_REQUIRE(b && bytes, "NULL argument");
+    PB_REQUIRE(nbytes == b->nbytes, "expected %llu bytes, got %llu", (unsigned long long)b->nbytes, (unsigned long long)nbytes);
+    DeviceGuard g(b->ctx->device);
+    PB_CUDA(cudaMemsetAsync(b->words, 0, b->nwords * 4, b->ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(b->words, bytes, nbytes, cudaMemcpyHostToDevice, b->ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return PB_OK;
+}
+
+int pb_bloom_download(pb_bloom *b, uint8_t *bytes, uint64_t nbytes) {
+    PB_REQUIRE(b && bytes, "NULL argument");
+    PB_REQUIRE(nbytes == b->nbytes, "expected %llu bytes, got %llu", (unsigned long long)b->nbytes, (unsigned long long)nbytes);
+    DeviceGuard g(b->ctx->device);
+    PB_CUDA(cudaMemcpyAsync(bytes, b->words, nbytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return PB_OK;
+}
+
+int pb_bloom_device_ptr(pb_bloom *b, void **out_dev, uint64_t *out_nbytes) {
+    PB_REQUIRE(b && out_dev, "NULL argument");
+    *out_dev = b->words;
+    if (out_nbytes) *out_nbytes = b->nbytes;
+    return PB_OK;
+}
+
+int pb_bloom_add_keys(pb_bloom *b, const pb_keys *keys) {
+    PB_REQUIRE(b && keys, "NULL argument");
+    DeviceGuard g(b->ctx->device);
+    PB_TRY(validate_keys(keys));
+    AddArgs a;
+    a.b = b;
+    const bool fixed16 = keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 &&
+                         (keys->on_device ? ((uintptr_t)keys->data & 15u) == 0 : true);
+    a.plan = plan_partition(b, keys->n, fixed16);
+    return for_each_chunk(b->ctx, keys, add_chunk, &a, a.plan.use ? a.plan.chunk_keys : 0);
+}
+
+int pb_bloom_check_keys(pb_bloom *b, const pb_keys *keys, uint8_t *out, int out_on_device) {
+    PB_REQUIRE(b && keys, "NULL argument");
+    PB_REQUIRE(out || keys->n == 0, "out is NULL");
+    DeviceGuard g(b->ctx->device);
+    CheckArgs a;
+    a.b = b;
+    a.out_dev = out_on_device ? out : nullptr;
+    a.out_host = out_on_device ? nullptr : out;
+    PB_TRY(for_each_chunk(b->ctx, keys, check_chunk, &a));
+    if (!out_on_device) PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return PB_OK;
+}
+
+static int stage_hashes(pb_ctx *ctx, const uint64_t *hashes, uint64_t count, int on_device, const uint64_t **dev) {
+    if (on_device) {
+        *dev = hashes;
+        return PB_OK;
+    }
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], count * 8));
+    PB_CUDA(cudaMemcpyAsync(ctx->aux_stage[0].p, hashes, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = (const uint64_t *)ctx->aux_stage[0].p;
+    return PB_OK;
+}
+
+int pb_bloom_add_hashes(pb_bloom *b, const uint64_t *hashes, uint64_t n, int on_device) {
+    PB_REQUIRE(b && (hashes || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    const uint64_t *d;
+    PB_TRY(stage_hashes(ctx, hashes, n * b->k, on_device, &d));
+    bloom_add_hashes_kernel<<<grid_for(ctx, n * b->k, 256, 8), 256, 0, ctx->stream>>>(d, n * b->k, dev_view(b));
+    PB_TRY(check_launch(ctx, "bloom_add_hashes"));
+    if (!on_device) PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_bloom_check_hashes(pb_bloom *b, const uint64_t *hashes, uint64_t n, int on_device, uint8_t *out, int out_on_device) {
+    PB_REQUIRE(b && ((hashes && out) || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    const uint64_t *d;
+    PB_TRY(stage_hashes(ctx, hashes, n * b->k, on_device, &d));
+    uint8_t *o = out;
+    if (!out_on_device) {
+        PB_TRY(scratch_reserve(ctx, ctx->out_stage[0], n));
+        o = (uint8_t *)ctx->out_stage[0].p;
+    }
+    bloom_check_hashes_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d, n, dev_view(b), o);
+    PB_TRY(check_launch(ctx, "bloom_check_hashes"));
+    if (!out_on_device) {
+        PB_CUDA(cudaMemcpyAsync(out, o, n, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}
+
+int pb_bloom_popcount(pb_bloom *b, uint64_t *out) {
+    PB_REQUIRE(b && out, "NULL argument");
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = (unsigned long long *)ctx->small.p;
+    PB_CUDA(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+    popcount_kernel<<<grid_for(ctx, b->nwords / 4, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)b->words, b->nwords / 4, acc);
+    PB_TRY(check_launch(ctx, "popcount"));
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = *(uint64_t *)ctx->pinned_small;
+    return PB_OK;
+}
+
+int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint64_t shard_bits,
+                        uint32_t n_shards, uint64_t *out_idx_dev, uint64_t slot_cap, uint64_t *counts_dev) {
+    PB_REQUIRE(ctx && keys && out_idx_dev && counts_dev, "NULL argument");
+    PB_REQUIRE(keys->on_device, "pb_bloom_route_keys takes device keys");
+    PB_REQUIRE(n_shards >= 1 && n_shards <= 64, "n_shards must be in 1..64");
+    PB_REQUIRE(shard_bits >= 1 && shard_bits * n_shards >= num_bits, "shards do not cover the filter");
+    PB_REQUIRE(keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 && ((uintptr_t)keys->data & 15u) == 0,
+               "routing currently takes fixed 16-byte keys");
+    PB_REQUIRE(k >= 1, "k must be >= 1");
+    DeviceGuard g(ctx->device);
+    if (keys->n == 0) return PB_OK;
+    FastMod fm = make_fastmod(num_bits);
+    FastMod sd = make_fastmod(shard_bits);
+    int st = PB_OK;
+    const int kg = pick_group(k);
+    const int grid = grid_for(ctx, keys->n, 256, 6);
+    launch_begin(ctx);
+#define CALL(K)                                                                                                       \
+    (bloom_route_fixed16<K><<<grid, 256, 0, ctx->stream>>>((const uint4 *)keys->data, keys->n, fm, k, sd, shard_bits, \
+                                                           n_shards, out_idx_dev, slot_cap,                           \
+                                                           (unsigned long long *)counts_dev),                         \
+     check_launch(ctx, "bloom_route"))
+    PB_DISPATCH_KG(kg, CALL)
+#undef CALL
+    return st;
+}
+
+int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n) {
+    PB_REQUIRE(b && (idx_dev || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *stray = (unsigned long long *)ctx->small.p + 8;
+    PB_CUDA(cudaMemsetAsync(stray, 0, 8, ctx->stream));
+    launch_begin(ctx);
+    bloom_add_idx_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, dev_view(b), stray);
+    PB_TRY(check_launch(ctx, "bloom_add_bit_indices"));
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, stray, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t bad = *(uint64_t *)ctx->pinned_small;
+    PB_REQUIRE(bad == 0, "%llu bit indices fell outside this shard", (unsigned long long)bad);
+    return PB_OK;
+}
+
+int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, uint8_t *out_dev) {
+    PB_REQUIRE(b && ((idx_dev && out_dev) || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    bloom_test_idx_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, dev_view(b), out_dev);
+    return check_launch(ctx, "bloom_test_bit_indices");
+}
+
+}  // extern "C"

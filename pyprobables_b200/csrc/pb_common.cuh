@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pb200.h"
 
@@ -46,6 +47,13 @@ struct pb_scratch {
     size_t cap = 0;
 };
 
+// one timed kernel launch (only while the "kernel_timing" option is on): events bracket the launch on
+// the compute stream; pb_ctx_kernel_times() resolves them
+struct pb_timed_launch {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+
 struct pb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   // compute stream (all kernels)
@@ -60,6 +68,11 @@ struct pb_ctx {
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics
+    int64_t cuckoo_serial = 0;           // 1: one-thread in-order cuckoo insert (reference append order)
+    int64_t kernel_timing = 0;           // 1: bracket the hot kernels with CUDA events (bench roofline)
+    std::vector<pb_timed_launch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t pending_e0 = nullptr;
     // reusable buffers
     pb_scratch key_stage[2];   // device staging of host key data (double buffered)
     pb_scratch off_stage[2];   // device staging of host offsets
@@ -101,8 +114,32 @@ inline int grid_for(const pb_ctx *ctx, uint64_t work_items, int block, int ctas_
     return (int)(need < cap ? need : cap);
 }
 
+inline cudaEvent_t timing_event(pb_ctx *ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->event_pool.empty()) {
+        e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+
+// call right before the <<<>>> of a kernel that should show up in pb_ctx_kernel_times()
+inline void launch_begin(pb_ctx *ctx) {
+    if (!ctx->kernel_timing || ctx->pending_e0) return;
+    ctx->pending_e0 = timing_event(ctx);
+    cudaEventRecord(ctx->pending_e0, ctx->stream);
+}
+
 inline int check_launch(pb_ctx *ctx, const char *what) {
     ctx->launches++;
+    if (ctx->pending_e0) {
+        pb_timed_launch t{what, ctx->pending_e0, timing_event(ctx)};
+        cudaEventRecord(t.e1, ctx->stream);
+        ctx->timed.push_back(t);
+        ctx->pending_e0 = nullptr;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("launch of %s failed: %s", what, cudaGetErrorString(e));

@@ -1,0 +1,790 @@
+// pb_cuckoo.cu -- CuckooFilter.add / check for whole batches
+// (reference: probables/cuckoo/cuckoo.py:291-315, :361-392, :440-453, :483-506; utilities.py:32-35).
+//
+// State: u32 slots[capacity][bucket_size], 0 = empty.  The reference keeps a Python list per bucket;
+// what `check` observes is only *which fingerprints are stored* -- both candidate buckets are a
+// function of the fingerprint alone (:483-490), so membership does not depend on slot placement or on
+// the random eviction choices (:373, :377).  That is the parity contract: the set of stored
+// fingerprints, elements_added (= number of distinct fingerprints placed) and every check() result.
+// Fingerprint 0 is legal (utilities.py:35) but equals "empty" in the flat layout (and in the
+// reference's own export format, :346/:429); it is kept as a one-word device flag.
+//
+// add() for a batch runs as three kernels:
+//   1. claim+filter  hash key -> fp (:499-500); one thread per *distinct* fp of the batch wins a claim
+//                    bit (atomicOr on a 2^fp_bits-bit scratch bitmap: exact in-batch dedupe); the winner
+//                    looks the fp up in its two buckets (:300-302, :440-446) and, when absent, appends
+//                    it to a compact list of fingerprints to insert.
+//   2. insert        one thread per new fp: CAS into the first empty slot of idx_1, then idx_2
+//                    (:363-368); otherwise the eviction walk of <= max_swaps steps (:371-389) with
+//                    atomicExch -- every fingerprint is always either in a slot or in exactly one
+//                    thread's hand, so nothing is duplicated or lost.  Walks that run out of swaps hand
+//                    their homeless fingerprint back to the caller (:392, :508-516).
+//   3. unclaim       clears the claim bits again (memset for big batches, per-fp for small ones).
+// Because kernel 2 only ever sees fingerprints that are distinct and absent, no presence check has to
+// race with an eviction in flight.
+// "cuckoo_serial" (context option) replaces 1-3 by a one-thread kernel that inserts in key order, which
+// reproduces the reference's append order (export bytes match at loads without evictions).
+#include <algorithm>
+#include <new>
+
+#include "pb_common.cuh"
+#include "pb_hash.cuh"
+#include "pb_keys.cuh"
+
+using namespace pb;
+
+struct pb_cuckoo {
+    pb_ctx *ctx = nullptr;
+    uint64_t capacity = 0;
+    uint32_t bucket_size = 0, max_swaps = 0, fp_bits = 0;
+    uint64_t rng_seed = 0;
+    uint64_t epoch = 0;  // bumps per insert launch so eviction choices differ between batches
+    uint32_t *slots = nullptr;
+    uint64_t nslots = 0;
+    uint32_t *zero_flag = nullptr;  // device word: 1 when fingerprint 0 is stored
+    uint32_t *claim = nullptr;      // 2^fp_bits bits of in-batch claim scratch
+    uint64_t claim_words = 0;
+    FastMod fm;
+};
+
+namespace pb {
+
+struct CuckooDev {
+    uint32_t *slots;
+    uint32_t *zero_flag;
+    uint32_t *claim;
+    FastMod fm;
+    uint32_t bucket_size, max_swaps, fp_bits;
+};
+
+struct CuckooCounters {  // device-resident, zeroed per call
+    unsigned long long n_new;     // fingerprints handed to the insert kernel
+    unsigned long long n_placed;  // fingerprints newly stored
+    unsigned long long n_failed;  // homeless fingerprints
+    unsigned long long pad;
+};
+
+__device__ __forceinline__ void cuckoo_buckets(const CuckooDev &c, uint32_t fp, uint64_t &i1, uint64_t &i2) {
+    i1 = fastmod((uint64_t)fp, c.fm);       // cuckoo.py:488
+    i2 = fastmod(fnv_of_decimal(fp), c.fm);  // cuckoo.py:489
+}
+
+// fp in bucket?  (cuckoo.py:442-445)
+template <int BS>
+__device__ __forceinline__ bool bucket_has(const CuckooDev &c, uint64_t b, uint32_t fp) {
+    if (BS == 4) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + b);
+        return v.x == fp || v.y == fp || v.z == fp || v.w == fp;
+    }
+    const uint32_t *s = c.slots + b * c.bucket_size;
+    bool hit = false;
+    for (uint32_t j = 0; j < c.bucket_size; ++j) hit |= (__ldcg(s + j) == fp);
+    return hit;
+}
+
+// cuckoo.py:448-453: put fp into the first empty slot of bucket b
+template <int BS>
+__device__ __forceinline__ bool bucket_place(const CuckooDev &c, uint64_t b, uint32_t fp) {
+    uint32_t *s = c.slots + b * c.bucket_size;
+    if (BS == 4) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + b);
+        if (v.x == 0 && atomicCAS(s + 0, 0u, fp) == 0u) return true;
+        if (v.y == 0 && atomicCAS(s + 1, 0u, fp) == 0u) return true;
+        if (v.z == 0 && atomicCAS(s + 2, 0u, fp) == 0u) return true;
+        if (v.w == 0 && atomicCAS(s + 3, 0u, fp) == 0u) return true;
+        return false;
+    }
+    for (uint32_t j = 0; j < c.bucket_size; ++j)
+        if (__ldcg(s + j) == 0u && atomicCAS(s + j, 0u, fp) == 0u) return true;
+    return false;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) { return sm64(x); }
+
+// cuckoo.py:361-392 for one fingerprint that is known to be absent.  Returns true when everything found
+// a home; false with `fp` = the homeless fingerprint.
+template <int BS>
+__device__ __forceinline__ bool cuckoo_insert_one(const CuckooDev &c, uint32_t &fp, uint64_t rng) {
+    uint64_t i1, i2;
+    cuckoo_buckets(c, fp, i1, i2);
+    if (bucket_place<BS>(c, i1, fp)) return true;  // :363-365
+    if (bucket_place<BS>(c, i2, fp)) return true;  // :366-368
+    rng = mix64(rng ^ fp);
+    uint64_t idx = (rng & 1ull) ? i2 : i1;  // :373
+    for (uint32_t s = 0; s < c.max_swaps; ++s) {
+        rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+        const uint32_t slot = (uint32_t)(((rng >> 33) * (uint64_t)c.bucket_size) >> 31);  // :377 (uniform in [0,bs))
+        const uint32_t victim = atomicExch(c.slots + idx * c.bucket_size + slot, fp);     // :379-380
+        if (victim == 0u) return true;  // the slot was (still) empty: nobody was evicted
+        fp = victim;
+        uint64_t a, b;
+        cuckoo_buckets(c, fp, a, b);  // :383
+        idx = (idx == a) ? b : a;     // :385
+        if (bucket_place<BS>(c, idx, fp)) return true;  // :387-388
+    }
+    return false;  // :392
+}
+
+// ---- kernel 1: key -> fp, in-batch claim, presence filter, compaction ------------------------------
+template <int BS>
+__device__ __forceinline__ void claim_filter(const CuckooDev &c, uint32_t fp, bool active, uint32_t *__restrict__ newlist,
+                                             CuckooCounters *cnt) {
+    bool is_new = false;
+    if (active) {
+        if (fp == 0u) {
+            // the zero fingerprint lives in the flag word; the flag itself is the claim
+            if (atomicExch(c.zero_flag, 1u) == 0u) atomicAdd(&cnt->n_placed, 1ull);
+        } else {
+            const uint32_t bit = 1u << (fp & 31u);
+            const uint32_t old = atomicOr(c.claim + (fp >> 5), bit);
+            if ((old & bit) == 0u) {  // this thread owns fp for the batch
+                uint64_t i1, i2;
+                cuckoo_buckets(c, fp, i1, i2);
+                is_new = !(bucket_has<BS>(c, i1, fp) || bucket_has<BS>(c, i2, fp));  // :300-302
+            }
+        }
+    }
+    // warp-aggregated append to the list of fingerprints to insert
+    const uint32_t m = __ballot_sync(0xffffffffu, is_new);
+    if (m) {
+        const uint32_t lane = threadIdx.x & 31u;
+        unsigned long long base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&cnt->n_new, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (is_new) newlist[base + __popc(m & ((1u << lane) - 1u))] = fp;
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) cuckoo_claim_fixed16(const uint4 *__restrict__ keys, uint64_t n, CuckooDev c,
+                                                            uint32_t *__restrict__ fps, uint32_t *__restrict__ newlist,
+                                                            CuckooCounters *cnt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (n + stride - 1) / stride;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t r = 0; r < rounds; ++r, i += stride) {
+        const bool active = i < n;
+        uint32_t fp = 0;
+        if (active) {
+            uint64_t h[1];
+            fnv_group_16<1>(__ldcs(keys + i), 0, h);
+            fp = cuckoo_fingerprint(h[0], c.fp_bits);  // :499-500
+            fps[i] = fp;
+        }
+        claim_filter<BS>(c, fp, active, newlist, cnt);
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) cuckoo_claim_fps(const uint32_t *__restrict__ fps, uint64_t n, CuckooDev c,
+                                                        uint32_t *__restrict__ newlist, CuckooCounters *cnt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (n + stride - 1) / stride;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t r = 0; r < rounds; ++r, i += stride) {
+        const bool active = i < n;
+        const uint32_t fp = active ? cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits) : 0u;
+        claim_filter<BS>(c, fp, active, newlist, cnt);
+    }
+}
+
+// generic keys: fingerprints only (the claim then runs from the fp array)
+template <int SYMW>
+__global__ void __launch_bounds__(kTileKeys) cuckoo_fp_staged(DevKeys dk, uint32_t fp_bits, uint32_t *__restrict__ fps) {
+    __shared__ TileSmem sm;
+    if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t first = tile * kTileKeys;
+        const uint32_t count = (uint32_t)min((uint64_t)kTileKeys, dk.n - first);
+        const KeyRef kr = stage_tile<SYMW>(dk, first, count, sm, parity);
+        if (threadIdx.x < count) {
+            uint64_t h[1];
+            fnv_group_ptr<1, SYMW>(kr.p, kr.len, 0, h);
+            fps[first + threadIdx.x] = cuckoo_fingerprint(h[0], fp_bits);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cuckoo_fp_fixed16(const uint4 *__restrict__ keys, uint64_t n, uint32_t fp_bits,
+                                                         uint32_t *__restrict__ fps) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h[1];
+        fnv_group_16<1>(__ldcs(keys + i), 0, h);
+        fps[i] = cuckoo_fingerprint(h[0], fp_bits);
+    }
+}
+
+// ---- kernel 2: insert distinct, absent fingerprints ---------------------------------------------------
+// skip_zero: the list is an old slot array (expand, :467-481) whose zeros are empty slots.
+template <int BS>
+__global__ void __launch_bounds__(256) cuckoo_insert_kernel(const uint32_t *__restrict__ list, const unsigned long long *n_ptr,
+                                                            uint64_t n_fixed, int skip_zero, CuckooDev c, uint64_t rng_seed,
+                                                            uint32_t *__restrict__ failed, uint64_t failed_cap, CuckooCounters *cnt) {
+    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
+    unsigned long long placed = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t fp = list[i];
+        if (skip_zero && fp == 0u) continue;
+        if (cuckoo_insert_one<BS>(c, fp, rng_seed + i * 0x9E3779B97F4A7C15ULL)) {
+            ++placed;
+        } else {
+            const unsigned long long pos = atomicAdd(&cnt->n_failed, 1ull);
+            if (pos < failed_cap) failed[pos] = fp;
+        }
+    }
+    if (placed) atomicAdd(&cnt->n_placed, placed);  // one per thread: noise next to the table traffic
+}
+
+// ---- kernel 3: release the claim bits of a small batch ---------------------------------------------------
+__global__ void __launch_bounds__(256) cuckoo_unclaim_kernel(const uint32_t *__restrict__ fps, uint64_t n, uint32_t fp_bits,
+                                                             uint32_t *claim) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], fp_bits);
+        claim[fp >> 5] = 0u;  // whole word: every bit of it that is set belongs to this batch
+    }
+}
+
+// ---- serial restatement on the device (one thread, key order) -----------------------------------------
+template <int BS>
+__global__ void cuckoo_serial_kernel(const uint32_t *__restrict__ fps, uint64_t n, CuckooDev c, uint64_t rng_seed,
+                                     uint32_t *__restrict__ failed, uint64_t failed_cap, CuckooCounters *cnt) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits);
+        if (fp == 0u) {
+            if (atomicExch(c.zero_flag, 1u) == 0u) cnt->n_placed++;
+            continue;
+        }
+        uint64_t i1, i2;
+        cuckoo_buckets(c, fp, i1, i2);
+        if (bucket_has<BS>(c, i1, fp) || bucket_has<BS>(c, i2, fp)) continue;
+        cnt->n_new++;
+        if (cuckoo_insert_one<BS>(c, fp, rng_seed + i * 0x9E3779B97F4A7C15ULL)) {
+            cnt->n_placed++;
+        } else {
+            if (cnt->n_failed < failed_cap) failed[cnt->n_failed] = fp;
+            cnt->n_failed++;
+        }
+        __threadfence();
+    }
+}
+
+// ---- check (cuckoo.py:306-315) ---------------------------------------------------------------------------
+template <int BS>
+__device__ __forceinline__ uint8_t cuckoo_lookup(const CuckooDev &c, uint32_t fp) {
+    if (fp == 0u) return (uint8_t)(__ldcg(c.zero_flag) != 0u);
+    uint64_t i1, i2;
+    cuckoo_buckets(c, fp, i1, i2);
+    // both bucket reads are issued before either is tested
+    const bool a = bucket_has<BS>(c, i1, fp);
+    const bool b = bucket_has<BS>(c, i2, fp);
+    return (uint8_t)(a | b);
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+    cuckoo_check_fixed16(const uint4 *__restrict__ keys, uint64_t n, CuckooDev c, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h[1];
+        fnv_group_16<1>(__ldcs(keys + i), 0, h);
+        out[i] = cuckoo_lookup<BS>(c, cuckoo_fingerprint(h[0], c.fp_bits));
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+    cuckoo_check_fps(const uint32_t *__restrict__ fps, uint64_t n, CuckooDev c, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = cuckoo_lookup<BS>(c, cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits));
+}
+
+// _generate_fingerprint_info (:492-506) from fingerprints
+__global__ void __launch_bounds__(256) cuckoo_info_kernel(const uint32_t *__restrict__ fps, uint64_t n, CuckooDev c,
+                                                          uint64_t *__restrict__ i1, uint64_t *__restrict__ i2) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        cuckoo_buckets(c, fps[i], i1[i], i2[i]);
+}
+
+__global__ void __launch_bounds__(256) count_nonzero_kernel(const uint32_t *__restrict__ s, uint64_t n, unsigned long long *out) {
+    unsigned long long c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        c += (s[i] != 0u);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// ---------------------------------------------------------------- host side
+static CuckooDev dev_view(const pb_cuckoo *c) {
+    CuckooDev d;
+    d.slots = c->slots;
+    d.zero_flag = c->zero_flag;
+    d.claim = c->claim;
+    d.fm = c->fm;
+    d.bucket_size = c->bucket_size;
+    d.max_swaps = c->max_swaps;
+    d.fp_bits = c->fp_bits;
+    return d;
+}
+
+#define PB_BS_DISPATCH(c, KERNEL, GRID, BLOCK, ...)                                               \
+    do {                                                                                          \
+        launch_begin((c)->ctx);                                                                   \
+        if ((c)->bucket_size == 4) KERNEL<4><<<GRID, BLOCK, 0, (c)->ctx->stream>>>(__VA_ARGS__);    \
+        else KERNEL<0><<<GRID, BLOCK, 0, (c)->ctx->stream>>>(__VA_ARGS__);                          \
+    } while (0)
+
+static int ensure_claim(pb_cuckoo *c) {
+    if (c->claim) return PB_OK;
+    c->claim_words = c->fp_bits >= 5 ? (1ull << (c->fp_bits - 5)) : 1ull;
+    cudaError_t e = cudaMalloc(&c->claim, c->claim_words * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c->claim = nullptr;
+        set_error("cudaMalloc of the %llu-byte claim bitmap failed: %s", (unsigned long long)(c->claim_words * 4),
+                  cudaGetErrorString(e));
+        return PB_ERR_OOM;
+    }
+    PB_CUDA(cudaMemsetAsync(c->claim, 0, c->claim_words * 4, c->ctx->stream));
+    return PB_OK;
+}
+
+// scratch layout inside ctx->small: [0] popcount, [8] stray, [16..17] cms sums, [32..35] CuckooCounters
+static CuckooCounters *counters_dev(pb_ctx *ctx) { return (CuckooCounters *)((unsigned long long *)ctx->small.p + 32); }
+
+struct CuckooResult {
+    uint64_t n_added = 0, n_failed = 0;
+    uint32_t *failed_out = nullptr;  // host
+    uint64_t failed_cap = 0, failed_written = 0;
+};
+
+// Inserts the fingerprints fps_dev[0..n) (device) with in-batch dedupe and presence filtering.
+// `fused_keys` != nullptr: kernel 1 hashes the fixed-16 keys itself and fills fps_dev.
+static int add_fps_device(pb_cuckoo *c, const uint4 *fused_keys, uint32_t *fps_dev, uint64_t n, int slot, CuckooResult *res) {
+    pb_ctx *ctx = c->ctx;
+    if (n == 0) return PB_OK;
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    CuckooCounters *cnt = counters_dev(ctx);
+    PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(CuckooCounters), ctx->stream));
+    // newlist and failed share one allocation: [newlist n][failed n]
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[slot], n * 8));
+    uint32_t *newlist = (uint32_t *)ctx->aux_stage[slot].p;
+    uint32_t *failed = newlist + n;
+    const CuckooDev cd = dev_view(c);
+    const uint64_t seed = c->rng_seed + (++c->epoch) * 0xD1B54A32D192ED03ULL;
+    if (ctx->cuckoo_serial) {
+        if (fused_keys) {
+            cuckoo_fp_fixed16<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(fused_keys, n, c->fp_bits, fps_dev);
+            PB_TRY(check_launch(ctx, "cuckoo_fp"));
+        }
+        PB_BS_DISPATCH(c, cuckoo_serial_kernel, 1, 32, fps_dev, n, cd, seed, failed, n, cnt);
+        PB_TRY(check_launch(ctx, "cuckoo_serial"));
+    } else {
+        PB_TRY(ensure_claim(c));
+        const CuckooDev cd2 = dev_view(c);
+        const int grid = grid_for(ctx, n, 256, 8);
+        if (fused_keys) PB_BS_DISPATCH(c, cuckoo_claim_fixed16, grid, 256, fused_keys, n, cd2, fps_dev, newlist, cnt);
+        else PB_BS_DISPATCH(c, cuckoo_claim_fps, grid, 256, fps_dev, n, cd2, newlist, cnt);
+        PB_TRY(check_launch(ctx, "cuckoo_claim"));
+        PB_BS_DISPATCH(c, cuckoo_insert_kernel, grid, 256, newlist, &cnt->n_new, 0, 0, cd2, seed, failed, n, cnt);
+        PB_TRY(check_launch(ctx, "cuckoo_insert"));
+        if (n * 64 < c->claim_words * 4) {
+            cuckoo_unclaim_kernel<<<grid, 256, 0, ctx->stream>>>(fps_dev, n, c->fp_bits, c->claim);
+            PB_TRY(check_launch(ctx, "cuckoo_unclaim"));
+        } else {
+            PB_CUDA(cudaMemsetAsync(c->claim, 0, c->claim_words * 4, ctx->stream));
+        }
+    }
+    // results (small D2H; this call is synchronous by contract because failures must be reported)
+    CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
+    PB_CUDA(cudaMemcpyAsync(h, cnt, sizeof(CuckooCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    res->n_added += h->n_placed;
+    if (h->n_failed) {
+        const uint64_t have = std::min<uint64_t>(h->n_failed, n);
+        const uint64_t room = res->failed_cap > res->failed_written ? res->failed_cap - res->failed_written : 0;
+        const uint64_t take = std::min(have, room);
+        if (take && res->failed_out) {
+            PB_CUDA(cudaMemcpyAsync(res->failed_out + res->failed_written, failed, take * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            res->failed_written += take;
+        }
+        res->n_failed += h->n_failed;
+    }
+    return PB_OK;
+}
+
+struct CuckooAddArgs {
+    pb_cuckoo *c;
+    CuckooResult *res;
+};
+
+static int cuckoo_add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    (void)first;
+    CuckooAddArgs *a = (CuckooAddArgs *)user;
+    pb_cuckoo *c = a->c;
+    PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n * 4));
+    uint32_t *fps = (uint32_t *)ctx->out_stage[slot].p;
+    if (is_fixed16(dk)) return add_fps_device(c, (const uint4 *)dk.data, fps, dk.n, slot, a->res);
+    const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+    if (dk.sym_width == 4) cuckoo_fp_staged<4><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+    else cuckoo_fp_staged<1><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+    PB_TRY(check_launch(ctx, "cuckoo_fp_staged"));
+    return add_fps_device(c, nullptr, fps, dk.n, slot, a->res);
+}
+
+struct CuckooCheckArgs {
+    pb_cuckoo *c;
+    uint8_t *out_dev;
+    uint8_t *out_host;
+};
+
+static int cuckoo_check_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    CuckooCheckArgs *a = (CuckooCheckArgs *)user;
+    pb_cuckoo *c = a->c;
+    const CuckooDev cd = dev_view(c);
+    uint8_t *out = a->out_dev ? a->out_dev + first : nullptr;
+    if (!out) {
+        PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n));
+        out = (uint8_t *)ctx->out_stage[slot].p;
+    }
+    if (is_fixed16(dk)) {
+        PB_BS_DISPATCH(c, cuckoo_check_fixed16, grid_for(ctx, dk.n, 256, 8), 256, (const uint4 *)dk.data, dk.n, cd, out);
+        PB_TRY(check_launch(ctx, "cuckoo_check"));
+    } else {
+        PB_TRY(scratch_reserve(ctx, ctx->aux_stage[slot], dk.n * 4));
+        uint32_t *fps = (uint32_t *)ctx->aux_stage[slot].p;
+        const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+        if (dk.sym_width == 4) cuckoo_fp_staged<4><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+        else cuckoo_fp_staged<1><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+        PB_TRY(check_launch(ctx, "cuckoo_fp_staged"));
+        PB_BS_DISPATCH(c, cuckoo_check_fps, grid_for(ctx, dk.n, 256, 8), 256, fps, dk.n, cd, out);
+        PB_TRY(check_launch(ctx, "cuckoo_check_fps"));
+    }
+    if (a->out_host) PB_CUDA(cudaMemcpyAsync(a->out_host + first, out, dk.n, cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
+struct CuckooInfoArgs {
+    pb_cuckoo *c;
+    uint32_t *fp;
+    uint64_t *i1, *i2;
+    int out_on_device;
+};
+
+static int cuckoo_info_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    CuckooInfoArgs *a = (CuckooInfoArgs *)user;
+    pb_cuckoo *c = a->c;
+    uint32_t *fps;
+    uint64_t *i1, *i2;
+    if (a->out_on_device) {
+        fps = a->fp + first;
+        i1 = a->i1 + first;
+        i2 = a->i2 + first;
+    } else {
+        PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n * 20 + 64));
+        i1 = (uint64_t *)ctx->out_stage[slot].p;
+        i2 = i1 + dk.n;
+        fps = (uint32_t *)(i2 + dk.n);
+    }
+    if (is_fixed16(dk)) {
+        cuckoo_fp_fixed16<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, c->fp_bits, fps);
+    } else {
+        const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+        if (dk.sym_width == 4) cuckoo_fp_staged<4><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+        else cuckoo_fp_staged<1><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+    }
+    PB_TRY(check_launch(ctx, "cuckoo_fp"));
+    cuckoo_info_kernel<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>(fps, dk.n, dev_view(c), i1, i2);
+    PB_TRY(check_launch(ctx, "cuckoo_info"));
+    if (!a->out_on_device) {
+        PB_CUDA(cudaMemcpyAsync(a->fp + first, fps, dk.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaMemcpyAsync(a->i1 + first, i1, dk.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaMemcpyAsync(a->i2 + first, i2, dk.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return PB_OK;
+}
+
+static int finish_add(int st, const CuckooResult &res, uint64_t *n_added, uint64_t *n_failed) {
+    if (n_added) *n_added = res.n_added;
+    if (n_failed) *n_failed = res.n_failed;
+    PB_TRY(st);
+    if (res.n_failed) {
+        set_error("The CuckooFilter is currently full (%llu fingerprints left homeless)", (unsigned long long)res.n_failed);
+        return PB_ERR_CUCKOO_FULL;
+    }
+    return PB_OK;
+}
+
+static int cuckoo_alloc_table(pb_ctx *ctx, uint64_t capacity, uint32_t bucket_size, uint32_t **slots, uint64_t *nslots) {
+    const uint64_t n = capacity * (uint64_t)bucket_size;
+    PB_REQUIRE(n / bucket_size == capacity && n < (1ull << 60), "capacity * bucket_size overflows");
+    const uint64_t alloc = (n + 3) & ~(uint64_t)3;
+    cudaError_t e = cudaMalloc(slots, alloc * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %llu cuckoo table bytes failed: %s", (unsigned long long)(alloc * 4), cudaGetErrorString(e));
+        return PB_ERR_OOM;
+    }
+    PB_CUDA(cudaMemsetAsync(*slots, 0, alloc * 4, ctx->stream));
+    *nslots = n;
+    return PB_OK;
+}
+
+}  // namespace pb
+
+extern "C" {
+
+int pb_cuckoo_create(pb_ctx *ctx, uint64_t capacity, uint32_t bucket_size, uint32_t max_swaps, uint32_t fp_bits, uint64_t rng_seed,
+                     pb_cuckoo **out) {
+    PB_REQUIRE(ctx && out, "NULL argument");
+    PB_REQUIRE(capacity >= 1 && bucket_size >= 1 && max_swaps >= 1,
+               "CuckooFilter: capacity, bucket_size, and max_swaps must be an integer greater than 0");
+    PB_REQUIRE(fp_bits >= 1 && fp_bits <= 32, "fingerprint size must be 1..32 bits (got %u)", fp_bits);
+    DeviceGuard g(ctx->device);
+    pb_cuckoo *c = new (std::nothrow) pb_cuckoo();
+    if (!c) return PB_ERR_OOM;
+    c->ctx = ctx;
+    c->capacity = capacity;
+    c->bucket_size = bucket_size;
+    c->max_swaps = max_swaps;
+    c->fp_bits = fp_bits;
+    c->rng_seed = rng_seed ? rng_seed : 0x9E3779B97F4A7C15ULL;
+    c->fm = make_fastmod(capacity);
+    int st = cuckoo_alloc_table(ctx, capacity, bucket_size, &c->slots, &c->nslots);
+    if (st != PB_OK) {
+        delete c;
+        return st;
+    }
+    if (cudaMalloc(&c->zero_flag, 256) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(c->slots);
+        delete c;
+        set_error("cudaMalloc failed");
+        return PB_ERR_OOM;
+    }
+    cudaMemsetAsync(c->zero_flag, 0, 256, ctx->stream);
+    *out = c;
+    return PB_OK;
+}
+
+int pb_cuckoo_destroy(pb_cuckoo *c) {
+    if (!c) return PB_OK;
+    DeviceGuard g(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    cudaFree(c->slots);
+    cudaFree(c->zero_flag);
+    if (c->claim) cudaFree(c->claim);
+    delete c;
+    return PB_OK;
+}
+
+int pb_cuckoo_clear(pb_cuckoo *c) {
+    PB_REQUIRE(c, "handle is NULL");
+    DeviceGuard g(c->ctx->device);
+    PB_CUDA(cudaMemsetAsync(c->slots, 0, ((c->nslots + 3) & ~(uint64_t)3) * 4, c->ctx->stream));
+    PB_CUDA(cudaMemsetAsync(c->zero_flag, 0, 4, c->ctx->stream));
+    return PB_OK;
+}
+
+int pb_cuckoo_add_keys(pb_cuckoo *c, const pb_keys *keys, uint64_t *n_added, uint64_t *n_failed, uint32_t *failed_fps,
+                       uint64_t failed_cap) {
+    PB_REQUIRE(c && keys, "NULL argument");
+    DeviceGuard g(c->ctx->device);
+    CuckooResult res;
+    res.failed_out = failed_fps;
+    res.failed_cap = failed_fps ? failed_cap : 0;
+    CuckooAddArgs a{c, &res};
+    // chunk so the per-chunk scratch (12 B/key) stays bounded for device-resident batches
+    const int st = for_each_chunk(c->ctx, keys, cuckoo_add_chunk, &a, 1ull << 28);
+    return finish_add(st, res, n_added, n_failed);
+}
+
+int pb_cuckoo_add_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, int on_device, uint64_t *n_added, uint64_t *n_failed,
+                               uint32_t *failed_fps, uint64_t failed_cap) {
+    PB_REQUIRE(c && (fps || n == 0), "NULL argument");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    CuckooResult res;
+    res.failed_out = failed_fps;
+    res.failed_cap = failed_fps ? failed_cap : 0;
+    int st = PB_OK;
+    const uint64_t step = 1ull << 28;
+    for (uint64_t c0 = 0; c0 < n && st == PB_OK; c0 += step) {
+        const uint64_t cn = std::min(step, n - c0);
+        uint32_t *d = const_cast<uint32_t *>(fps) + c0;
+        if (!on_device) {
+            st = scratch_reserve(ctx, ctx->out_stage[0], cn * 4);
+            if (st != PB_OK) break;
+            d = (uint32_t *)ctx->out_stage[0].p;
+            cudaError_t e = cudaMemcpyAsync(d, fps + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) {
+                set_error("H2D copy failed: %s", cudaGetErrorString(e));
+                st = PB_ERR_CUDA;
+                break;
+            }
+        }
+        st = add_fps_device(c, nullptr, d, cn, 0, &res);
+    }
+    return finish_add(st, res, n_added, n_failed);
+}
+
+int pb_cuckoo_check_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device) {
+    PB_REQUIRE(c && keys, "NULL argument");
+    PB_REQUIRE(out || keys->n == 0, "out is NULL");
+    DeviceGuard g(c->ctx->device);
+    CuckooCheckArgs a{c, out_on_device ? out : nullptr, out_on_device ? nullptr : out};
+    PB_TRY(for_each_chunk(c->ctx, keys, cuckoo_check_chunk, &a));
+    if (!out_on_device) PB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    return PB_OK;
+}
+
+int pb_cuckoo_check_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, int on_device, uint8_t *out, int out_on_device) {
+    PB_REQUIRE(c && ((fps && out) || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    const uint32_t *d = fps;
+    if (!on_device) {
+        PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 4));
+        PB_CUDA(cudaMemcpyAsync(ctx->aux_stage[0].p, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d = (const uint32_t *)ctx->aux_stage[0].p;
+    }
+    uint8_t *o = out;
+    if (!out_on_device) {
+        PB_TRY(scratch_reserve(ctx, ctx->out_stage[0], n));
+        o = (uint8_t *)ctx->out_stage[0].p;
+    }
+    const CuckooDev cd = dev_view(c);
+    PB_BS_DISPATCH(c, cuckoo_check_fps, grid_for(ctx, n, 256, 8), 256, d, n, cd, o);
+    PB_TRY(check_launch(ctx, "cuckoo_check_fps"));
+    if (!out_on_device) {
+        PB_CUDA(cudaMemcpyAsync(out, o, n, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}
+
+int pb_cuckoo_fingerprint_info(pb_cuckoo *c, const pb_keys *keys, uint32_t *fp, uint64_t *idx1, uint64_t *idx2, int out_on_device) {
+    PB_REQUIRE(c && keys, "NULL argument");
+    PB_REQUIRE((fp && idx1 && idx2) || keys->n == 0, "NULL output");
+    DeviceGuard g(c->ctx->device);
+    CuckooInfoArgs a{c, fp, idx1, idx2, out_on_device};
+    // host outputs are copied back per chunk from per-slot scratch: keep chunks in step with the slots
+    PB_TRY(for_each_chunk(c->ctx, keys, cuckoo_info_chunk, &a));
+    if (!out_on_device) PB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    return PB_OK;
+}
+
+int pb_cuckoo_count(pb_cuckoo *c, uint64_t *out) {
+    PB_REQUIRE(c && out, "NULL argument");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = (unsigned long long *)ctx->small.p;
+    PB_CUDA(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+    count_nonzero_kernel<<<grid_for(ctx, c->nslots, 256, 8), 256, 0, ctx->stream>>>(c->slots, c->nslots, acc);
+    PB_TRY(check_launch(ctx, "cuckoo_count"));
+    uint64_t *h = (uint64_t *)ctx->pinned_small;
+    PB_CUDA(cudaMemcpyAsync(h, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(h + 1, c->zero_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = h[0] + (((uint32_t *)(h + 1))[0] ? 1u : 0u);
+    return PB_OK;
+}
+
+int pb_cuckoo_download(pb_cuckoo *c, uint32_t *slots, uint64_t count, int *has_zero_fp) {
+    PB_REQUIRE(c && (slots || count == 0), "NULL argument");
+    PB_REQUIRE(count == c->nslots || (count == 0 && !slots), "expected %llu slots, got %llu", (unsigned long long)c->nslots,
+               (unsigned long long)count);
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    if (count) PB_CUDA(cudaMemcpyAsync(slots, c->slots, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t *h = (uint32_t *)ctx->pinned_small;
+    PB_CUDA(cudaMemcpyAsync(h, c->zero_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (has_zero_fp) *has_zero_fp = h[0] ? 1 : 0;
+    return PB_OK;
+}
+
+int pb_cuckoo_upload(pb_cuckoo *c, const uint32_t *slots, uint64_t count, int has_zero_fp) {
+    PB_REQUIRE(c && slots, "NULL argument");
+    PB_REQUIRE(count == c->nslots, "expected %llu slots, got %llu", (unsigned long long)c->nslots, (unsigned long long)count);
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_CUDA(cudaMemcpyAsync(c->slots, slots, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *h = (uint32_t *)ctx->pinned_small;
+    h[0] = has_zero_fp ? 1u : 0u;
+    PB_CUDA(cudaMemcpyAsync(c->zero_flag, h, 4, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_cuckoo_device_ptr(pb_cuckoo *c, void **out_dev, uint64_t *out_count) {
+    PB_REQUIRE(c && out_dev, "NULL argument");
+    *out_dev = c->slots;
+    if (out_count) *out_count = c->nslots;
+    return PB_OK;
+}
+
+int pb_cuckoo_capacity(pb_cuckoo *c, uint64_t *out) {
+    PB_REQUIRE(c && out, "NULL argument");
+    *out = c->capacity;
+    return PB_OK;
+}
+
+// cuckoo.py:455-481: capacity becomes new_capacity, every stored fingerprint is re-inserted from scratch.
+int pb_cuckoo_expand(pb_cuckoo *c, uint64_t new_capacity, uint64_t *n_failed, uint32_t *failed_fps, uint64_t failed_cap) {
+    PB_REQUIRE(c, "handle is NULL");
+    PB_REQUIRE(new_capacity >= 1, "new capacity must be >= 1");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    uint32_t *old_slots = c->slots;
+    const uint64_t old_n = c->nslots;
+    uint32_t *new_slots = nullptr;
+    uint64_t new_n = 0;
+    PB_TRY(cuckoo_alloc_table(ctx, new_capacity, c->bucket_size, &new_slots, &new_n));
+    c->slots = new_slots;
+    c->nslots = new_n;
+    c->capacity = new_capacity;
+    c->fm = make_fastmod(new_capacity);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    CuckooCounters *cnt = counters_dev(ctx);
+    PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(CuckooCounters), ctx->stream));
+    const uint64_t fcap = std::max<uint64_t>(failed_cap, 1);
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], fcap * 4));
+    uint32_t *failed = (uint32_t *)ctx->aux_stage[0].p;
+    const uint64_t seed = c->rng_seed + (++c->epoch) * 0xD1B54A32D192ED03ULL;
+    const CuckooDev cd = dev_view(c);
+    if (ctx->cuckoo_serial) {
+        // one thread walks the old slot array in bucket order, like :467-481
+        PB_BS_DISPATCH(c, cuckoo_insert_kernel, 1, 1, old_slots, nullptr, old_n, 1, cd, seed, failed, fcap, cnt);
+    } else {
+        PB_BS_DISPATCH(c, cuckoo_insert_kernel, grid_for(ctx, old_n, 256, 8), 256, old_slots, nullptr, old_n, 1, cd, seed, failed,
+                       fcap, cnt);
+    }
+    PB_TRY(check_launch(ctx, "cuckoo_expand"));
+    CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
+    PB_CUDA(cudaMemcpyAsync(h, cnt, sizeof(CuckooCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(cudaFree(old_slots));
+    if (n_failed) *n_failed = h->n_failed;
+    if (h->n_failed) {
+        const uint64_t take = std::min<uint64_t>(h->n_failed, failed_fps ? failed_cap : 0);
+        if (take) {
+            PB_CUDA(cudaMemcpyAsync(failed_fps, failed, take * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        set_error("The CuckooFilter failed to expand (%llu fingerprints left homeless)", (unsigned long long)h->n_failed);
+        return PB_ERR_CUCKOO_FULL;
+    }
+    return PB_OK;
+}
+
+}  // extern "C"

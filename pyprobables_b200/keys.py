@@ -1,0 +1,124 @@
+"""Packing of key batches into the pb_keys layout (include/pb200.h).
+
+A key is what the reference calls KeyT = str | bytes (probables/hashes.py:10).  The reference hashes a
+`str` per code point -- `list(map(ord, key))`, hashes.py:98 -- and `bytes` per byte, so:
+  * bytes / bytearray / memoryview      -> one u8 symbol per byte
+  * str whose code points are all < 256  -> one u8 symbol per character (latin-1 bytes, NOT utf-8)
+  * a batch holding a str with a code point >= 256 -> the whole batch is packed as u32 symbols
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from ._native import pb_keys
+
+
+class KeyBatch:
+    """a packed batch; owns (references) the buffers the pb_keys struct points into"""
+
+    __slots__ = ("c", "n", "_keep", "on_device")
+
+    def __init__(self, data_ptr: int, offsets_ptr: int | None, n: int, stride: int, sym_width: int, on_device: bool, keep):
+        self.c = pb_keys(data_ptr or None, offsets_ptr or None, n, stride, sym_width, 1 if on_device else 0, 0)
+        self.n = n
+        self.on_device = on_device
+        self._keep = keep
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def _is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _pack_sequence(keys: Sequence) -> KeyBatch:
+    n = len(keys)
+    lens = np.empty(n, dtype=np.uint64)
+    parts: list[bytes] = []
+    wide = False
+    for i, k in enumerate(keys):
+        if isinstance(k, str):
+            if k.isascii():
+                b = k.encode("ascii")
+            else:
+                try:
+                    b = k.encode("latin-1")
+                except UnicodeEncodeError:
+                    wide = True
+                    break
+        elif isinstance(k, (bytes, bytearray, memoryview)):
+            b = bytes(k)
+        else:
+            raise TypeError(f"keys must be str or bytes-like, not {type(k).__name__}")
+        parts.append(b)
+        lens[i] = len(b)
+    if wide:
+        return _pack_sequence_wide(keys)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    data = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    if n and (lens == lens[0]).all() and lens[0] > 0:
+        # equal-length keys: the fixed-stride layout (16-byte keys take the register fast path)
+        return KeyBatch(data.ctypes.data, None, n, int(lens[0]), 1, False, (data,))
+    return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, n, 0, 1, False, (data, offsets))
+
+
+def _pack_sequence_wide(keys: Sequence) -> KeyBatch:
+    n = len(keys)
+    lens = np.empty(n, dtype=np.uint64)
+    parts: list[np.ndarray] = []
+    for i, k in enumerate(keys):
+        if isinstance(k, str):
+            a = np.frombuffer(k.encode("utf-32-le", "surrogatepass"), dtype="<u4")
+        elif isinstance(k, (bytes, bytearray, memoryview)):
+            a = np.frombuffer(bytes(k), dtype=np.uint8).astype("<u4")
+        else:
+            raise TypeError(f"keys must be str or bytes-like, not {type(k).__name__}")
+        parts.append(a)
+        lens[i] = a.size
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    data = np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0, dtype="<u4"), dtype="<u4")
+    return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, n, 0, 4, False, (data, offsets))
+
+
+def pack_keys(keys) -> KeyBatch:
+    """list/tuple of str|bytes, a single str|bytes (one key), a 2-D uint8 numpy array [n, L],
+    a 2-D uint8 CUDA torch tensor [n, L] (zero-copy, device resident), an existing KeyBatch, or a
+    (packed uint8 buffer, uint64 offsets[n+1]) pair -> KeyBatch"""
+    if isinstance(keys, KeyBatch):
+        return keys
+    if isinstance(keys, (str, bytes, bytearray, memoryview)):
+        return _pack_sequence([keys])
+    if isinstance(keys, np.ndarray):
+        if keys.dtype != np.uint8 or keys.ndim != 2:
+            raise TypeError("a numpy key batch must be a 2-D uint8 array [n_keys, key_len]")
+        a = np.ascontiguousarray(keys)
+        return KeyBatch(a.ctypes.data if a.size else None, None, a.shape[0], a.shape[1], 1, False, (a,))
+    if _is_torch_tensor(keys):
+        import torch
+
+        if keys.dtype != torch.uint8 or keys.dim() != 2:
+            raise TypeError("a torch key batch must be a 2-D uint8 tensor [n_keys, key_len]")
+        t = keys.contiguous()
+        if t.is_cuda:
+            return KeyBatch(t.data_ptr(), None, t.shape[0], t.shape[1], 1, True, (t,))
+        return KeyBatch(t.data_ptr(), None, t.shape[0], t.shape[1], 1, False, (t,))
+    if isinstance(keys, tuple) and len(keys) == 2 and isinstance(keys[0], np.ndarray) and isinstance(keys[1], np.ndarray):
+        data = np.ascontiguousarray(keys[0], dtype=np.uint8)
+        offsets = np.ascontiguousarray(keys[1], dtype=np.uint64)
+        if offsets.ndim != 1 or offsets.size < 1:
+            raise TypeError("offsets must be a 1-D uint64 array of n+1 entries")
+        if offsets.size > 1 and (np.diff(offsets.astype(np.int64)) < 0).any():
+            raise ValueError("offsets must be non-decreasing")
+        if int(offsets[-1]) > data.size:
+            raise ValueError("offsets run past the end of the packed buffer")
+        return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, offsets.size - 1, 0, 1, False, (data, offsets))
+    if isinstance(keys, Iterable):
+        return _pack_sequence(list(keys))
+    raise TypeError(f"cannot interpret {type(keys).__name__} as a batch of keys")
