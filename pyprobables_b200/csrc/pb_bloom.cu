@@ -467,7 +467,7 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
                 return PB_ERR_UNSUPPORTED;
         }
         PB_TRY(st);
-        const uint32_t cpw = (uint32_t)ctx->num_sms * 2;
+        const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
         launch_begin(ctx);
         bloom_apply_windows<<<pl.n_windows * cpw, 256, 0, ctx->stream>>>(bd, pd, cpw);
         return check_launch(ctx, "bloom_apply_windows");

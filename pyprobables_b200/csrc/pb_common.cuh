@@ -65,6 +65,8 @@ struct pb_ctx {
     // options
     int64_t bloom_insert_mode = 0;       // 0 auto, 1 direct, 2 partitioned
     int64_t bloom_window_log2_bits = 28; // 2^28 bits = 32 MiB of bitmap per L2 window
+    int64_t bloom_apply_cpw_per_sm = 8;  // apply pass: CTAs per window = this x SMs; 8 = every resident CTA slot, so one
+                                         // 32 MiB window is in flight at a time and stays L2 resident (4 at once thrash: r1 sweep)
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics

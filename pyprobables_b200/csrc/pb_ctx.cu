@@ -419,6 +419,7 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "bloom_insert_mode")) return &ctx->bloom_insert_mode;
     if (!strcmp(name, "bloom_window_log2_bits")) return &ctx->bloom_window_log2_bits;
     if (!strcmp(name, "stage_bytes")) return &ctx->stage_bytes;
+    if (!strcmp(name, "bloom_apply_cpw_per_sm")) return &ctx->bloom_apply_cpw_per_sm;
     if (!strcmp(name, "h2d_chunk_keys")) return &ctx->h2d_chunk_keys;
     if (!strcmp(name, "cms_aggregate")) return &ctx->cms_aggregate;
     if (!strcmp(name, "cuckoo_serial")) return &ctx->cuckoo_serial;

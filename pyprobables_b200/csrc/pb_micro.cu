@@ -40,6 +40,28 @@ __global__ void __launch_bounds__(256) micro_random(uint32_t *__restrict__ words
     if (OP == 2 && acc == 0x12345679u) atomicAdd(sink, 1ull);
 }
 
+// op 4: atomicOr into a CTA-private shared-memory tile (2^20 bits) at random bit positions: the ceiling of
+// a shared-memory apply pass.  idx values are reused as bit positions (mod tile bits).
+__global__ void __launch_bounds__(1024) micro_smem_or(const uint32_t *__restrict__ idx, uint64_t n, unsigned long long *sink) {
+    extern __shared__ uint32_t tile[];
+    constexpr uint32_t kWords = 32768;  // 128 KB
+    for (uint32_t i = threadIdx.x; i < kWords; i += blockDim.x) tile[i] = 0;
+    __syncthreads();
+    const uint64_t n4 = n >> 2;
+    const uint4 *idx4 = reinterpret_cast<const uint4 *>(idx);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(idx4 + i);
+        atomicOr(tile + ((v.x >> 5) & (kWords - 1)), 1u << (v.x & 31));
+        atomicOr(tile + ((v.y >> 5) & (kWords - 1)), 1u << (v.y & 31));
+        atomicOr(tile + ((v.z >> 5) & (kWords - 1)), 1u << (v.z & 31));
+        atomicOr(tile + ((v.w >> 5) & (kWords - 1)), 1u << (v.w & 31));
+    }
+    __syncthreads();
+    uint32_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < kWords; i += blockDim.x) acc += __popc(tile[i]);
+    if (acc == 0xFFFFFFFFu) atomicAdd(sink, 1ull);
+}
+
 __global__ void __launch_bounds__(256) micro_copy(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n4) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x)
         __stcs(dst + i, __ldcs(src + i));
@@ -53,7 +75,7 @@ extern "C" {
 // Returns the best device time of `reps` runs (after one warm-up) in *ms_best.
 int pb_microbench_random_atomic(pb_ctx *ctx, uint64_t words, uint64_t n, int op, int reps, float *ms_best) {
     PB_REQUIRE(ctx && ms_best, "NULL argument");
-    PB_REQUIRE(op >= 0 && op <= 3, "op must be 0..3");
+    PB_REQUIRE(op >= 0 && op <= 4, "op must be 0..4");
     PB_REQUIRE(words >= 4 && words <= 0xFFFFFFFFull, "words must be in 4..2^32-1");
     PB_REQUIRE(reps >= 1, "reps must be >= 1");
     DeviceGuard g(ctx->device);
@@ -90,6 +112,10 @@ int pb_microbench_random_atomic(pb_ctx *ctx, uint64_t words, uint64_t n, int op,
                 case 0: micro_random<0><<<grid, 256, 0, ctx->stream>>>(buf, idx, n, sink); break;
                 case 1: micro_random<1><<<grid, 256, 0, ctx->stream>>>(buf, idx, n, sink); break;
                 case 2: micro_random<2><<<grid, 256, 0, ctx->stream>>>(buf, idx, n, sink); break;
+                case 4:
+                    cudaFuncSetAttribute(micro_smem_or, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+                    micro_smem_or<<<ctx->num_sms, 1024, 131072, ctx->stream>>>(idx, n, sink);
+                    break;
                 default: micro_copy<<<grid, 256, 0, ctx->stream>>>((const uint4 *)buf, (uint4 *)dst, words4 / 4); break;
             }
             ctx->launches++;
