@@ -319,9 +319,10 @@ static inline void cuckoo_indices(uint32_t fp, uint64_t capacity, uint64_t *i1, 
 
 void orc_cuckoo_fingerprint_info(const orc_keys *keys, uint64_t capacity, uint32_t fp_bits, uint32_t *fp,
                                  uint64_t *idx1, uint64_t *idx2) {
-    for (uint64_t i = 0; i < keys->n; ++i) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)keys->n; ++i) {
         uint64_t beg, len;
-        key_span(keys, i, &beg, &len);
+        key_span(keys, (uint64_t)i, &beg, &len);
         fp[i] = cuckoo_fp(fnv1a_syms(keys, beg, len, 0), fp_bits);
         cuckoo_indices(fp[i], capacity, &idx1[i], &idx2[i]);
     }
