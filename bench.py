@@ -319,21 +319,27 @@ def run_ours(args) -> None:
         roof = None
         atomic = None
         if ktimes:
-            dom = max(ktimes.items(), key=lambda kv: kv[1][1])
-            name, (n_launch, tot_ms) = dom
+            name, (n_launch, tot_ms) = max(ktimes.items(), key=lambda kv: kv[1][1])
             keys_per_launch = n_keys * args.steps / max(n_launch, 1)
-            # algorithmic bytes per key (DESIGN.md / SURVEY 8d): the random-atomic model of the whole insert
+            # algorithmic bytes of a Bloom insert = key + k random 32-B-sector read-modify-writes
             algo_per_key = 16 + 64 * k
-            design = {"bloom_add": 16 + 64 * k, "bloom_part": 16 + 4 * k, "bloom_apply_windows": 4 * k,
-                      "bloom_route": 16 + 8 * k, "bloom_add_bit_indices": 8 + 64}
-            per_key = design.get(name, algo_per_key)
+            # what the kernels of this design actually have to move per key: pass 1 reads the key and
+            # writes k 4-byte indices, pass 2 reads them back; the bitmap is read+written once per chunk
+            n_chunks = max(1, ktimes.get("bloom_apply_windows", (1, 0))[0] // max(args.steps, 1))
+            design_per_key = 16 + 8 * k + 2.0 * bitmap_bytes * n_chunks / n_keys if "bloom_part" in ktimes else algo_per_key
             avg_ms = tot_ms / max(n_launch, 1)
-            achieved = keys_per_launch * per_key / (avg_ms * 1e-3) / 1e9
+            achieved = keys_per_launch * algo_per_key / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_key": per_key, "launches": n_launch, "avg_launch_ms": avg_ms,
-                    "kernel_share_of_step": tot_ms / ms,
+                    "algorithmic_bytes_per_key": algo_per_key, "keys_per_launch": keys_per_launch,
+                    "launches": n_launch, "avg_launch_ms": avg_ms, "kernel_share_of_step": tot_ms / ms,
                     "kernels": {kn: {"launches": v[0], "total_ms": v[1]} for kn, v in ktimes.items()},
+                    "note": ("achieved = SURVEY 8(d) algorithmic bytes (16+64k per key, the random-atomic model) x keys per launch / "
+                             "average launch time of the dominant kernel; pass 2 (bloom_apply_windows) runs concurrently on a second "
+                             "stream, so the kernel times overlap.  The partitioned design moves far fewer DRAM bytes than the model "
+                             "(design_bytes_per_key), which is how it exceeds the random-atomic ceiling."),
+                    "design_bytes_per_key": design_per_key,
+                    "design_achieved_GBps": value / world * design_per_key / 1e9,
                     "step_model": {"survey_bytes_per_key": algo_per_key,
                                    "achieved_GBps": value / world * algo_per_key / 1e9,
                                    "frac": value / world * algo_per_key / 1e9 / hbm_peak}}

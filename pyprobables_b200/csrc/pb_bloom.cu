@@ -20,6 +20,7 @@
 #include "pb_common.cuh"
 #include "pb_hash.cuh"
 #include "pb_keys.cuh"
+#include "pb_bloom_part.cuh"
 
 using namespace pb;
 
@@ -372,6 +373,9 @@ struct PartPlan {
     uint64_t cap = 0;
     uint64_t chunk_keys = 0;
     int kg = 0, ng = 0;
+    int version = 3;  // 1: bloom_part_fixed16 + bloom_apply_windows, 2/3: pb_bloom_part.cuh
+    int halves = 1;   // 2: the staging is split in two so pass 2 of one chunk overlaps pass 1 of the next
+    int grid = 0;     // CTAs of the pass-1 launch (the v2 staging slack depends on it)
 };
 
 // Decide whether (and how) a batch of n keys goes through the partitioned path.
@@ -388,21 +392,36 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
         if (b->nbytes <= l2) return pl;
         if ((double)n * b->k * 64.0 < 4.0 * (double)b->nbytes) return pl;
     }
+    const int version = ctx->bloom_part_version == 1 ? 1 : (ctx->bloom_part_version == 2 ? 2 : 3);
+    const uint32_t wl_max = version >= 2 ? 31 : 32;
+    const uint64_t max_windows = version >= 2 ? (uint64_t)kMaxWindows2 : (uint64_t)kMaxWindows;
     uint32_t wl = (uint32_t)ctx->bloom_window_log2_bits;
-    if (wl > 32) wl = 32;
-    while (((b->num_bits + ((1ull << wl) - 1)) >> wl) > (uint64_t)kMaxWindows && wl < 32) ++wl;
+    if (wl > wl_max) wl = wl_max;
+    while (((b->num_bits + ((1ull << wl) - 1)) >> wl) > max_windows && wl < wl_max) ++wl;
     const uint64_t nw = (b->num_bits + ((1ull << wl) - 1)) >> wl;
-    if (nw > (uint64_t)kMaxWindows || wl < 5) return pl;
+    if (nw > max_windows || wl < 5) return pl;
     uint64_t stage_items = (uint64_t)ctx->stage_bytes / 4;
+    // overlap only pays when the batch needs more than one chunk anyway or is big enough to split in two
+    const int halves = (version >= 2 && ctx->bloom_overlap && n >= (1ull << 24)) ? 2 : 1;
+    stage_items /= (uint64_t)halves;
+    if (version >= 2 && stage_items > 0xFFFFFFF0ull) stage_items = 0xFFFFFFF0ull;  // 32-bit entry numbers
     uint64_t cap = (stage_items / nw) & ~(uint64_t)3;
     const double per_key_per_window = (double)b->k * (double)(1ull << wl) / (double)b->num_bits;  // <= k
+    const int grid = grid_for(ctx, n, 256, version >= 2 ? 4 : 6);
+    // room every window needs beyond its expected share: statistical slack + (v2) the partly used quotas
+    const double slack = 8192.0 + (version >= 2 ? (double)grid * (double)kQuota : 0.0);
     // shrink the staging to what this batch needs
-    uint64_t need = (uint64_t)((double)n * std::min(per_key_per_window, (double)b->k) * 1.03) + 8192;
+    uint64_t need = (uint64_t)((double)n * std::min(per_key_per_window, (double)b->k) * 1.03 + slack);
     need = (need + 3) & ~(uint64_t)3;
     if (need < cap) cap = need;
-    if (cap < 16384) return pl;
-    uint64_t chunk = (uint64_t)(((double)cap - 8192.0) / 1.03 / std::min(per_key_per_window, (double)b->k));
+    if ((double)cap < 2.0 * slack + 16384.0) return pl;
+    uint64_t chunk = (uint64_t)(((double)cap - slack) / 1.03 / std::min(per_key_per_window, (double)b->k));
+    if (version >= 2) chunk = std::min<uint64_t>(chunk, (0xF0000000ull - (uint64_t)grid * kQuota) / b->k);  // u32 cursors
+    if (halves == 2) chunk = std::min<uint64_t>(chunk, (n + 3) / 4);  // at least four chunks to pipeline
+    pl.halves = halves;
     if (chunk < 1024) return pl;
+    pl.version = version;
+    pl.grid = grid;
     pl.use = true;
     pl.window_log2 = wl;
     pl.n_windows = (uint32_t)nw;
@@ -428,6 +447,8 @@ static int launch_part(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd, const
 struct AddArgs {
     pb_bloom *b;
     PartPlan plan;
+    uint64_t chunk_no = 0;
+    bool overlapped = false;  // pass 2 launches went to ctx->aux_stream: join before returning
 };
 
 static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
@@ -437,6 +458,71 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
     pb_bloom *b = a->b;
     const BloomDev bd = dev_view(b);
     int st = PB_OK;
+    if (a->plan.use && a->plan.version >= 2 && is_fixed16(dk)) {
+        const PartPlan &pl = a->plan;
+        const bool overlap = pl.halves == 2;
+        const int half = overlap ? (int)(a->chunk_no++ & 1) : 0;
+        const size_t half_entries = (size_t)pl.n_windows * pl.cap;
+        PB_TRY(scratch_reserve(ctx, ctx->part_stage, half_entries * 4 * (size_t)pl.halves));
+        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, (size_t)kMaxWindows * 8));
+        Part2Dev pd;
+        pd.stage = (uint32_t *)ctx->part_stage.p + (size_t)half * half_entries;
+        pd.cursors = (unsigned int *)ctx->part_cursors.p + (size_t)half * kMaxWindows2;
+        pd.words = b->words;
+        pd.m = b->num_bits;
+        pd.recip = b->fm.recip;
+        pd.cap = (uint32_t)pl.cap;
+        pd.window_log2 = pl.window_log2;
+        pd.n_windows = pl.n_windows;
+        pd.k = b->k;
+        pd.recip_fits32 = b->num_bits > (1ull << 32) ? 1u : 0u;
+        // this half of the staging is free again once the pass 2 that read it last has finished
+        if (overlap && ctx->apply_pending[half]) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[half], 0));
+        PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 4, ctx->stream));
+        const int grid = std::min(pl.grid, grid_for(ctx, dk.n, 256, 4));
+        const uint4 *k4 = (const uint4 *)dk.data;
+        launch_begin(ctx);
+        switch (pl.ng * 100 + pl.kg) {
+#define PB_P2(KG, NG)                                                                                   \
+    do {                                                                                                \
+        if (pl.version == 2) bloom_part2_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd);    \
+        else bloom_part3_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd);                    \
+    } while (0)
+            case 101: PB_P2(1, 1); break;
+            case 102: PB_P2(2, 1); break;
+            case 103: PB_P2(3, 1); break;
+            case 104: PB_P2(4, 1); break;
+            case 105: PB_P2(5, 1); break;
+            case 106: PB_P2(6, 1); break;
+            case 107: PB_P2(7, 1); break;
+            case 108: PB_P2(8, 1); break;
+            case 205: PB_P2(5, 2); break;
+            case 206: PB_P2(6, 2); break;
+            case 207: PB_P2(7, 2); break;
+            case 208: PB_P2(8, 2); break;
+#undef PB_P2
+            default:
+                set_error("internal: no partition kernel for k=%u", b->k);
+                return PB_ERR_UNSUPPORTED;
+        }
+        PB_TRY(check_launch(ctx, "bloom_part"));
+        const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
+        cudaStream_t s2 = ctx->stream;
+        if (overlap) {
+            s2 = ctx->aux_stream;
+            PB_CUDA(cudaEventRecord(ctx->ev_part[half], ctx->stream));
+            PB_CUDA(cudaStreamWaitEvent(s2, ctx->ev_part[half], 0));
+        }
+        launch_begin(ctx, s2);
+        bloom_apply2<<<pl.n_windows * cpw, 256, 0, s2>>>(pd, cpw);
+        PB_TRY(check_launch(ctx, "bloom_apply_windows", s2));
+        if (overlap) {
+            PB_CUDA(cudaEventRecord(ctx->ev_apply[half], s2));
+            ctx->apply_pending[half] = true;
+            a->overlapped = true;
+        }
+        return PB_OK;
+    }
     if (a->plan.use && is_fixed16(dk)) {
         const PartPlan &pl = a->plan;
         PB_TRY(scratch_reserve(ctx, ctx->part_stage, (size_t)pl.n_windows * pl.cap * 4));
@@ -600,7 +686,19 @@ int pb_bloom_add_keys(pb_bloom *b, const pb_keys *keys) {
     const bool fixed16 = keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 &&
                          (keys->on_device ? ((uintptr_t)keys->data & 15u) == 0 : true);
     a.plan = plan_partition(b, keys->n, fixed16);
-    return for_each_chunk(b->ctx, keys, add_chunk, &a, a.plan.use ? a.plan.chunk_keys : 0);
+    pb_ctx *ctx = b->ctx;
+    const int st = for_each_chunk(ctx, keys, add_chunk, &a, a.plan.use ? a.plan.chunk_keys : 0);
+    if (a.overlapped) {
+        // later work on the context's stream (checks, popcount, downloads) must see every pass 2
+        for (int h = 0; h < 2; ++h) {
+            if (ctx->apply_pending[h]) {
+                PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[h], 0));
+                ctx->apply_pending[h] = false;
+            }
+        }
+        if (!keys->on_device) PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return st;
 }
 
 int pb_bloom_check_keys(pb_bloom *b, const pb_keys *keys, uint8_t *out, int out_on_device) {

@@ -1,0 +1,304 @@
+// pb_bloom_part.cuh -- second generation of the partitioned Bloom insert (pass 1 + pass 2).
+//
+// Same idea as bloom_part_fixed16 / bloom_apply_windows in pb_bloom.cu (bin the bit indices of a chunk of
+// keys by L2-sized bitmap window, then apply window by window), rebuilt around what the round-1 ncu profile
+// of the first version showed (issue slots 35 % busy; stalls: shared-memory atomics' results and constant
+// reloads 27 %, the un-prefetched key load 19 %, three CTA barriers per tile 17 %, and a global cursor
+// atomic round trip inside every tile):
+//   * window cursors are reserved in quotas: a CTA takes kQuota list entries of a window at a time with ONE
+//     global atomic and hands them out from shared memory, so most tiles touch no global atomic at all.
+//     Entries of a quota a CTA does not use are filled with kSentinel, which pass 2 skips;
+//   * histogram and tile bases ping-pong between two shared-memory copies: two barriers per tile instead of
+//     three, and the zeroing rides along in the serial section;
+//   * the next tile's key is loaded before the current one is hashed;
+//   * list positions are 32-bit entry numbers relative to one base pointer (no 64-bit pointer math per bit);
+//   * h % m uses a 32-bit reciprocal when m > 2^32 (every filter large enough to take this path): two
+//     IMAD.WIDE instead of four for the high product.
+// The result is exact for any input: a position beyond a window's capacity falls back to a direct RED.OR.
+#pragma once
+#include "pb_common.cuh"
+#include "pb_hash.cuh"
+#include "pb_keys.cuh"
+
+namespace pb {
+
+constexpr uint32_t kSentinel = 0xFFFFFFFFu;  // never a valid window-local bit index (windows are <= 2^31 bits)
+constexpr uint32_t kQuota = 1024;            // list entries a CTA reserves per window and refill
+constexpr int kMaxWindows2 = 512;
+
+struct Part2Dev {
+    uint32_t *stage;         // n_windows * cap entries
+    unsigned int *cursors;   // n_windows, entries reserved so far per window (may run past cap)
+    uint32_t *words;         // the bitmap (overflow fallback)
+    uint64_t m;              // number of bits (modulus)
+    uint64_t recip;          // floor(2^64 / m)
+    uint32_t cap;            // entries per window list
+    uint32_t window_log2;    // <= 31
+    uint32_t n_windows;
+    uint32_t k;
+    uint32_t recip_fits32;   // m > 2^32
+};
+
+// exact h % m with R = floor(2^64/m) < 2^32 (m > 2^32): q = floor(h*R / 2^64) is floor(h/m) or one less
+__device__ __forceinline__ uint64_t mod_big(uint64_t h, uint64_t m, uint32_t r32) {
+    const uint64_t t = (uint64_t)(uint32_t)h * r32;
+    const uint64_t u = (h >> 32) * (uint64_t)r32 + (t >> 32);
+    const uint32_t q = (uint32_t)(u >> 32);
+    uint64_t r = h - (uint64_t)q * m;
+    return r >= m ? r - m : r;
+}
+
+__device__ __forceinline__ uint64_t mod_any(uint64_t h, const Part2Dev &p) {
+    if (p.recip_fits32) return mod_big(h, p.m, (uint32_t)p.recip);
+    const uint64_t q = __umul64hi(h, p.recip);
+    const uint64_t r = h - q * p.m;
+    return r >= p.m ? r - p.m : r;
+}
+
+template <int KG, int NG>
+__global__ void __launch_bounds__(256, 4) bloom_part2_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p) {
+    __shared__ uint32_t hist[2][kMaxWindows2];
+    __shared__ uint32_t tbase[2][kMaxWindows2];  // absolute entry number (w*cap + pos) of the tile's first entry
+    __shared__ uint32_t cur[kMaxWindows2], lim[kMaxWindows2];  // window-relative: next free / end of quota
+    const uint32_t tid = threadIdx.x;
+    const uint32_t W = p.n_windows;
+    const uint32_t mask = (1u << p.window_log2) - 1u;
+    for (uint32_t w = tid; w < W; w += blockDim.x) {
+        hist[0][w] = 0;
+        hist[1][w] = 0;
+        cur[w] = 0;
+        lim[w] = 0;
+    }
+    __syncthreads();
+    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t pp = 0;
+    uint64_t tile = blockIdx.x;
+    uint4 nextk = make_uint4(0, 0, 0, 0);
+    if (tile < tiles && tile * blockDim.x + tid < n) nextk = __ldcs(keys + tile * blockDim.x + tid);
+    for (; tile < tiles; tile += gridDim.x) {
+        const uint64_t i = tile * blockDim.x + tid;
+        const bool live = i < n;
+        const uint4 kw = nextk;
+        {
+            const uint64_t ni = (tile + gridDim.x) * blockDim.x + tid;
+            if (ni < n) nextk = __ldcs(keys + ni);
+        }
+        uint32_t loc[NG * KG];
+        uint32_t wr[NG * KG];  // window << 16 | rank within the tile
+        if (live) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                uint64_t h[KG];
+                fnv_group_16<KG>(kw, g * KG, h);
+#pragma unroll
+                for (int j = 0; j < KG; ++j) {
+                    if ((uint32_t)(g * KG + j) < p.k) {
+                        const uint64_t idx = mod_any(h[j], p);
+                        const uint32_t w = (uint32_t)(idx >> p.window_log2);
+                        loc[g * KG + j] = (uint32_t)idx & mask;
+                        wr[g * KG + j] = (w << 16) | atomicAdd(&hist[pp][w], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t w = tid; w < W; w += blockDim.x) {
+            const uint32_t need = hist[pp][w];
+            uint32_t c = cur[w];
+            if (need) {
+                uint32_t e = lim[w];
+                if (c + need > e) {
+                    // hand back what is left of the old quota as sentinels, then reserve a new one
+                    const uint32_t stop = e < p.cap ? e : p.cap;
+                    for (uint32_t q = c; q < stop; ++q) p.stage[w * p.cap + q] = kSentinel;
+                    const uint32_t take = need > kQuota ? need : kQuota;
+                    c = atomicAdd(p.cursors + w, take);
+                    lim[w] = c + take;
+                }
+                cur[w] = c + need;
+            }
+            tbase[pp][w] = c;
+            hist[pp ^ 1][w] = 0;
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int s = 0; s < NG * KG; ++s) {
+                if ((uint32_t)s < p.k) {
+                    const uint32_t w = wr[s] >> 16;
+                    const uint32_t pos = tbase[pp][w] + (wr[s] & 0xFFFFu);
+                    if (pos < p.cap) {
+                        __stcs(p.stage + (w * p.cap + pos), loc[s]);
+                    } else {  // window list full (skewed keys): straight to the bitmap
+                        const uint64_t idx = ((uint64_t)w << p.window_log2) | loc[s];
+                        atomicOr(p.words + (idx >> 5), 1u << (uint32_t)(idx & 31));
+                    }
+                }
+            }
+        }
+        pp ^= 1;
+    }
+    __syncthreads();
+    for (uint32_t w = tid; w < W; w += blockDim.x) {
+        const uint32_t e = lim[w] < p.cap ? lim[w] : p.cap;
+        for (uint32_t q = cur[w]; q < e; ++q) p.stage[w * p.cap + q] = kSentinel;
+    }
+}
+
+// ---- third generation: same bookkeeping as bloom_part2_fixed16, but the tile's indices are first sorted by
+// window in shared memory and then copied out by consecutive threads, so a warp's 32 stores fall into one to
+// three contiguous runs instead of ~20 scattered 4-byte writes.  The round-1 profiles showed pass 1 pinned
+// at ~45 G L2 write requests/s whatever the window count (time grew with the number of windows because the
+// requests per store instruction did); coalesced runs cut the requests by ~8x and make the cost independent
+// of the window count.
+template <int KG, int NG>
+__global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p) {
+    __shared__ uint32_t hist[2][kMaxWindows2];
+    __shared__ uint32_t tbase[kMaxWindows2];       // window-relative list position of the tile's first entry
+    __shared__ uint32_t wstart[kMaxWindows2 + 1];  // exclusive prefix sum of hist: start of the window's run in sorted[]
+    __shared__ uint32_t cur[kMaxWindows2], lim[kMaxWindows2];
+    __shared__ uint32_t sorted_loc[256 * NG * KG];
+    __shared__ uint16_t sorted_win[256 * NG * KG];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t W = p.n_windows;
+    const uint32_t mask = (1u << p.window_log2) - 1u;
+    for (uint32_t w = tid; w < W; w += blockDim.x) {
+        hist[0][w] = 0;
+        hist[1][w] = 0;
+        cur[w] = 0;
+        lim[w] = 0;
+    }
+    __syncthreads();
+    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t pp = 0;
+    uint64_t tile = blockIdx.x;
+    uint4 nextk = make_uint4(0, 0, 0, 0);
+    if (tile < tiles && tile * blockDim.x + tid < n) nextk = __ldcs(keys + tile * blockDim.x + tid);
+    const uint32_t per_lane = (W + 31) / 32;
+    for (; tile < tiles; tile += gridDim.x) {
+        const uint64_t i = tile * blockDim.x + tid;
+        const bool live = i < n;
+        const uint4 kw = nextk;
+        {
+            const uint64_t ni = (tile + gridDim.x) * blockDim.x + tid;
+            if (ni < n) nextk = __ldcs(keys + ni);
+        }
+        uint32_t loc[NG * KG];
+        uint32_t wr[NG * KG];  // window << 16 | rank within the tile
+        if (live) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                uint64_t h[KG];
+                fnv_group_16<KG>(kw, g * KG, h);
+#pragma unroll
+                for (int j = 0; j < KG; ++j) {
+                    if ((uint32_t)(g * KG + j) < p.k) {
+                        const uint64_t idx = mod_any(h[j], p);
+                        const uint32_t w = (uint32_t)(idx >> p.window_log2);
+                        loc[g * KG + j] = (uint32_t)idx & mask;
+                        wr[g * KG + j] = (w << 16) | atomicAdd(&hist[pp][w], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // warp 0: exclusive scan of the histogram (lane l owns windows [l*per_lane, (l+1)*per_lane))
+            uint32_t sum = 0;
+            const uint32_t w0 = tid * per_lane;
+            for (uint32_t q = 0; q < per_lane; ++q)
+                if (w0 + q < W) sum += hist[pp][w0 + q];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)tid >= o) incl += v;
+            }
+            uint32_t run = incl - sum;
+            for (uint32_t q = 0; q < per_lane; ++q) {
+                if (w0 + q < W) {
+                    wstart[w0 + q] = run;
+                    run += hist[pp][w0 + q];
+                }
+            }
+            if (tid == 31) wstart[W] = incl;
+        } else {
+            for (uint32_t w = tid - 32; w < W; w += blockDim.x - 32) {
+                const uint32_t need = hist[pp][w];
+                uint32_t c = cur[w];
+                if (need) {
+                    const uint32_t e = lim[w];
+                    if (c + need > e) {
+                        const uint32_t stop = e < p.cap ? e : p.cap;
+                        for (uint32_t q = c; q < stop; ++q) p.stage[w * p.cap + q] = kSentinel;
+                        const uint32_t take = need > kQuota ? need : kQuota;
+                        c = atomicAdd(p.cursors + w, take);
+                        lim[w] = c + take;
+                    }
+                    cur[w] = c + need;
+                }
+                tbase[w] = c;
+            }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int s = 0; s < NG * KG; ++s) {
+                if ((uint32_t)s < p.k) {
+                    const uint32_t w = wr[s] >> 16;
+                    const uint32_t e = wstart[w] + (wr[s] & 0xFFFFu);
+                    sorted_loc[e] = loc[s];
+                    sorted_win[e] = (uint16_t)w;
+                }
+            }
+        }
+        // the other histogram copy was last read in the serial section of the previous tile
+        for (uint32_t w = tid; w < W; w += blockDim.x) hist[pp ^ 1][w] = 0;
+        __syncthreads();
+        const uint32_t total = wstart[W];
+        for (uint32_t e = tid; e < total; e += blockDim.x) {
+            const uint32_t w = sorted_win[e];
+            const uint32_t pos = tbase[w] + (e - wstart[w]);
+            const uint32_t v = sorted_loc[e];
+            if (pos < p.cap) {
+                __stcs(p.stage + (w * p.cap + pos), v);
+            } else {
+                const uint64_t idx = ((uint64_t)w << p.window_log2) | v;
+                atomicOr(p.words + (idx >> 5), 1u << (uint32_t)(idx & 31));
+            }
+        }
+        pp ^= 1;
+    }
+    __syncthreads();
+    for (uint32_t w = tid; w < W; w += blockDim.x) {
+        const uint32_t e = lim[w] < p.cap ? lim[w] : p.cap;
+        for (uint32_t q = cur[w]; q < e; ++q) p.stage[w * p.cap + q] = kSentinel;
+    }
+}
+
+// pass 2: one window at a time (launch order); its bitmap slice stays L2 resident while its list streams by
+__global__ void __launch_bounds__(256) bloom_apply2(Part2Dev p, uint32_t ctas_per_window) {
+    const uint32_t w = blockIdx.x / ctas_per_window;
+    const uint32_t c = blockIdx.x % ctas_per_window;
+    uint32_t cnt = p.cursors[w];
+    if (cnt > p.cap) cnt = p.cap;
+    uint32_t *words = p.words + ((uint64_t)w << (p.window_log2 - 5));
+    const uint32_t *list = p.stage + (uint64_t)w * p.cap;
+    const uint32_t n4 = cnt >> 2;
+    const uint4 *list4 = reinterpret_cast<const uint4 *>(list);
+    for (uint32_t i = c * blockDim.x + threadIdx.x; i < n4; i += ctas_per_window * blockDim.x) {
+        const uint4 v = __ldcs(list4 + i);
+        if (v.x != kSentinel) atomicOr(words + (v.x >> 5), 1u << (v.x & 31));
+        if (v.y != kSentinel) atomicOr(words + (v.y >> 5), 1u << (v.y & 31));
+        if (v.z != kSentinel) atomicOr(words + (v.z >> 5), 1u << (v.z & 31));
+        if (v.w != kSentinel) atomicOr(words + (v.w >> 5), 1u << (v.w & 31));
+    }
+    if (c == 0) {
+        for (uint32_t i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t v = list[i];
+            if (v != kSentinel) atomicOr(words + (v >> 5), 1u << (v & 31));
+        }
+    }
+}
+
+}  // namespace pb

@@ -59,14 +59,20 @@ struct pb_ctx {
     cudaStream_t stream = nullptr;   // compute stream (all kernels)
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // H2D staging for host-buffer batches
+    cudaStream_t aux_stream = nullptr;   // pass 2 of the partitioned Bloom insert (overlaps pass 1 of the next chunk)
+    cudaEvent_t ev_part[2] = {nullptr, nullptr};   // pass 1 of the chunk using staging half i is done
+    cudaEvent_t ev_apply[2] = {nullptr, nullptr};  // pass 2 ... is done (the half may be refilled)
+    bool apply_pending[2] = {false, false};
     int num_sms = pb::kNumSMsB200;
     size_t l2_bytes = 0;
     uint64_t launches = 0;
     // options
     int64_t bloom_insert_mode = 0;       // 0 auto, 1 direct, 2 partitioned
-    int64_t bloom_window_log2_bits = 28; // 2^28 bits = 32 MiB of bitmap per L2 window
-    int64_t bloom_apply_cpw_per_sm = 8;  // apply pass: CTAs per window = this x SMs; 8 = every resident CTA slot, so one
-                                         // 32 MiB window is in flight at a time and stays L2 resident (4 at once thrash: r1 sweep)
+    int64_t bloom_window_log2_bits = 27; // 2^27 bits = 16 MiB of bitmap per L2 window (r1 sweeps: best with overlap)
+    int64_t bloom_apply_cpw_per_sm = 4;  // apply pass: CTAs per window = this x SMs (at most ~2 windows in flight, so the
+                                         // windows being updated stay L2 resident; 4 x 32 MiB at once thrashed: r1 sweep)
+    int64_t bloom_overlap = 1;           // run pass 2 of chunk i on aux_stream while pass 1 of chunk i+1 runs
+    int64_t bloom_part_version = 3;      // 1: first partition kernels, 2: quota cursors + prefetch, 3: + smem-sorted coalesced copy-out
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics
@@ -128,17 +134,17 @@ inline cudaEvent_t timing_event(pb_ctx *ctx) {
 }
 
 // call right before the <<<>>> of a kernel that should show up in pb_ctx_kernel_times()
-inline void launch_begin(pb_ctx *ctx) {
+inline void launch_begin(pb_ctx *ctx, cudaStream_t on = nullptr) {
     if (!ctx->kernel_timing || ctx->pending_e0) return;
     ctx->pending_e0 = timing_event(ctx);
-    cudaEventRecord(ctx->pending_e0, ctx->stream);
+    cudaEventRecord(ctx->pending_e0, on ? on : ctx->stream);
 }
 
-inline int check_launch(pb_ctx *ctx, const char *what) {
+inline int check_launch(pb_ctx *ctx, const char *what, cudaStream_t on = nullptr) {
     ctx->launches++;
     if (ctx->pending_e0) {
         pb_timed_launch t{what, ctx->pending_e0, timing_event(ctx)};
-        cudaEventRecord(t.e1, ctx->stream);
+        cudaEventRecord(t.e1, on ? on : ctx->stream);
         ctx->timed.push_back(t);
         ctx->pending_e0 = nullptr;
     }

@@ -28,6 +28,7 @@ int scratch_reserve(pb_ctx *ctx, pb_scratch &s, size_t bytes) {
         // buffers may still be in flight on the streams of this context
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
         PB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->aux_stream) PB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
         PB_CUDA(cudaFree(s.p));
         s.p = nullptr;
         s.cap = 0;
@@ -314,7 +315,10 @@ int pb_ctx_create(int device, void *stream, pb_ctx **out) {
         c->own_stream = true;
     }
     PB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    PB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
+        PB_CUDA(cudaEventCreateWithFlags(&c->ev_part[i], cudaEventDisableTiming));
+        PB_CUDA(cudaEventCreateWithFlags(&c->ev_apply[i], cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
@@ -328,7 +332,10 @@ int pb_ctx_destroy(pb_ctx *ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_part[i]) cudaEventDestroy(ctx->ev_part[i]);
+        if (ctx->ev_apply[i]) cudaEventDestroy(ctx->ev_apply[i]);
         scratch_release(ctx->key_stage[i]);
         scratch_release(ctx->off_stage[i]);
         scratch_release(ctx->aux_stage[i]);
@@ -349,6 +356,7 @@ int pb_ctx_destroy(pb_ctx *ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->pending_e0) cudaEventDestroy(ctx->pending_e0);
     cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PB_OK;
@@ -359,6 +367,7 @@ int pb_ctx_synchronize(pb_ctx *ctx) {
     DeviceGuard g(ctx->device);
     PB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
     return PB_OK;
 }
 
@@ -420,6 +429,8 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "bloom_window_log2_bits")) return &ctx->bloom_window_log2_bits;
     if (!strcmp(name, "stage_bytes")) return &ctx->stage_bytes;
     if (!strcmp(name, "bloom_apply_cpw_per_sm")) return &ctx->bloom_apply_cpw_per_sm;
+    if (!strcmp(name, "bloom_part_version")) return &ctx->bloom_part_version;
+    if (!strcmp(name, "bloom_overlap")) return &ctx->bloom_overlap;
     if (!strcmp(name, "h2d_chunk_keys")) return &ctx->h2d_chunk_keys;
     if (!strcmp(name, "cms_aggregate")) return &ctx->cms_aggregate;
     if (!strcmp(name, "cuckoo_serial")) return &ctx->cuckoo_serial;
