@@ -395,7 +395,7 @@ def run_ours(args) -> None:
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": (f"BloomFilter est_elements={EST_PER_GPU * world:.0e} fpr={FPR} (m={m} bits, k={k}); "
                                     f"step = clear + batch insert of {n_keys} 16-byte keys per GPU resident in HBM"
-                                    + ("" if world == 1 else f"; bit array range-sharded over {world} GPUs, NCCL all-to-all of bit indices ({args.shard_mode})")),
+                                    + ("" if world == 1 else f"; bit array range-sharded over {world} GPUs, NCCL all-to-all of window-partitioned bit indices ({args.shard_mode})")),
                        "keys_per_gpu_per_step": n_keys, "key_bytes": 16, "bitmap_bytes_per_gpu": int(bitmap_bytes),
                        "l2_policy": f"inputs larger than L2: {n_keys * 16} key bytes + {int(bitmap_bytes)} bitmap bytes per step vs 126 MB L2",
                        "insert_mode": int(ctx.get_option("bloom_insert_mode"))},
@@ -418,7 +418,7 @@ def main() -> None:
     ap.add_argument("--e2e-keys", type=int, default=1 << 27)
     ap.add_argument("--ref-keys", type=int, default=100_000, help="keys per step of the pure-Python reference arm")
     ap.add_argument("--chunk-keys", type=int, default=1 << 25)
-    ap.add_argument("--shard-mode", default="route", choices=["route", "gather"])
+    ap.add_argument("--shard-mode", default="fused", choices=["fused", "route", "gather"])
     ap.add_argument("--insert-mode", type=int, default=0, help="bloom_insert_mode: 0 auto, 1 direct RED, 2 partitioned")
     ap.add_argument("--window-log2", type=int, default=0, help="bloom_window_log2_bits override")
     ap.add_argument("--no-e2e", action="store_true")

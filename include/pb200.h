@@ -132,6 +132,19 @@ int pb_bloom_create_shard(pb_ctx *ctx, uint64_t num_bits, uint32_t k, uint64_t l
  * All buffers are device pointers (they feed an NCCL all-to-all). */
 int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint64_t shard_bits,
                         uint32_t n_shards, uint64_t *out_idx_dev, uint64_t slot_cap, uint64_t *counts_dev);
+/* Fused route + partition (the fast multi-GPU insert): hash -> % num_bits -> bin by GLOBAL window of
+ * 2^window_log2 bits (window g belongs to rank g / windows_per_rank) as window-local u32 into
+ * stage_dev[n_windows][cap], counts in cursors_dev[n_windows] (they may exceed cap; entries past cap went to
+ * ovf_list_dev as global u64 indices, *ovf_count_dev counts them).  One equal-split all-to-all of stage_dev
+ * and cursors_dev delivers every rank its windows; pb_bloom_apply_window_lists ORs them into the shard.
+ * Stream-ordered, no host synchronization.  pb_bloom_partition_slack: entries a list needs beyond its
+ * expected share. */
+int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
+                            uint32_t n_windows, uint32_t cap, uint32_t *stage_dev, uint32_t *cursors_dev,
+                            uint64_t *ovf_list_dev, uint64_t ovf_cap, uint64_t *ovf_count_dev);
+int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint64_t *out_entries);
+int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const uint32_t *cursors_dev, uint32_t n_sources,
+                                uint32_t windows_per_source, uint32_t windows, uint32_t cap, uint32_t window_log2);
 /* apply global bit indices that fall into this shard's [lo, hi) (others are an error count) */
 int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n);
 int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, uint8_t *out_dev);

@@ -476,6 +476,9 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
         pd.n_windows = pl.n_windows;
         pd.k = b->k;
         pd.recip_fits32 = b->num_bits > (1ull << 32) ? 1u : 0u;
+        pd.ovf_list = nullptr;
+        pd.ovf_count = nullptr;
+        pd.ovf_cap = 0;
         // this half of the staging is free again once the pass 2 that read it last has finished
         if (overlap && ctx->apply_pending[half]) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[half], 0));
         PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 4, ctx->stream));
@@ -799,6 +802,92 @@ int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uin
     PB_DISPATCH_KG(kg, CALL)
 #undef CALL
     return st;
+}
+
+// Multi-GPU fused route + partition: hash the keys, reduce % num_bits and bin the indices by GLOBAL window
+// (window g = idx >> window_log2 belongs to rank g / windows_per_rank) into stage_dev[n_windows][cap] as
+// window-local u32, counts in cursors_dev[n_windows].  The per-destination blocks of stage_dev are contiguous,
+// so one equal-split all-to-all delivers them.  Everything stays on the context's stream (no host sync).
+int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
+                            uint32_t n_windows, uint32_t cap, uint32_t *stage_dev, uint32_t *cursors_dev, uint64_t *ovf_list_dev,
+                            uint64_t ovf_cap, uint64_t *ovf_count_dev) {
+    PB_REQUIRE(ctx && keys && stage_dev && cursors_dev && ovf_list_dev && ovf_count_dev, "NULL argument");
+    PB_REQUIRE(keys->on_device, "pb_bloom_partition_keys takes device keys");
+    PB_REQUIRE(keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 && ((uintptr_t)keys->data & 15u) == 0,
+               "partitioned routing takes fixed 16-byte keys");
+    PB_REQUIRE(k >= 1 && k <= 16, "k must be in 1..16");
+    PB_REQUIRE(window_log2 >= 5 && window_log2 <= 31, "window_log2 must be in 5..31");
+    PB_REQUIRE(n_windows >= 1 && n_windows <= (uint32_t)kMaxWindows2, "n_windows must be in 1..%d", kMaxWindows2);
+    PB_REQUIRE(((uint64_t)n_windows << window_log2) >= num_bits, "windows do not cover the filter");
+    PB_REQUIRE((cap & 3u) == 0 && (uint64_t)cap * n_windows <= 0xFFFFFFF0ull, "cap must be a multiple of 4 and cap*n_windows < 2^32");
+    PB_REQUIRE(((uintptr_t)stage_dev & 15u) == 0, "stage_dev must be 16-byte aligned");
+    PB_REQUIRE(keys->n * (uint64_t)k < 0xE0000000ull, "too many keys for one partition call");
+    DeviceGuard g(ctx->device);
+    PB_CUDA(cudaMemsetAsync(cursors_dev, 0, (size_t)n_windows * 4, ctx->stream));
+    if (keys->n == 0) return PB_OK;
+    Part2Dev pd;
+    pd.stage = stage_dev;
+    pd.cursors = cursors_dev;
+    pd.words = nullptr;
+    pd.m = num_bits;
+    pd.recip = make_fastmod(num_bits).recip;
+    pd.cap = cap;
+    pd.window_log2 = window_log2;
+    pd.n_windows = n_windows;
+    pd.k = k;
+    pd.recip_fits32 = num_bits > (1ull << 32) ? 1u : 0u;
+    pd.ovf_list = ovf_list_dev;
+    pd.ovf_count = (unsigned long long *)ovf_count_dev;
+    pd.ovf_cap = ovf_cap;
+    const int grid = grid_for(ctx, keys->n, 256, 4);
+    const uint4 *k4 = (const uint4 *)keys->data;
+    const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
+    launch_begin(ctx);
+    switch (ng * 100 + kg) {
+#define PB_P3(KG, NG) bloom_part3_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, keys->n, pd)
+        case 101: PB_P3(1, 1); break;
+        case 102: PB_P3(2, 1); break;
+        case 103: PB_P3(3, 1); break;
+        case 104: PB_P3(4, 1); break;
+        case 105: PB_P3(5, 1); break;
+        case 106: PB_P3(6, 1); break;
+        case 107: PB_P3(7, 1); break;
+        case 108: PB_P3(8, 1); break;
+        case 205: PB_P3(5, 2); break;
+        case 206: PB_P3(6, 2); break;
+        case 207: PB_P3(7, 2); break;
+        case 208: PB_P3(8, 2); break;
+#undef PB_P3
+        default: set_error("internal: no partition kernel for k=%u", k); return PB_ERR_UNSUPPORTED;
+    }
+    return check_launch(ctx, "bloom_part");
+}
+
+// Slack a window list needs beyond its expected share for a pb_bloom_partition_keys call of n keys
+// (partly used quotas of every CTA of the launch); callers size `cap` with it.
+int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint64_t *out_entries) {
+    PB_REQUIRE(ctx && out_entries, "NULL argument");
+    *out_entries = (uint64_t)grid_for(ctx, n_keys, 256, 4) * kQuota + 8192;
+    return PB_OK;
+}
+
+// Pass 2 on this shard for lists received from n_sources ranks: stage_dev[n_sources][windows_per_source][cap],
+// cursors_dev[n_sources][windows_per_source]; the first `windows` of every block are this shard's (a short last
+// shard has fewer than windows_per_source); window w covers the shard's bits [w << window_log2, ...).
+int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const uint32_t *cursors_dev, uint32_t n_sources,
+                                uint32_t windows_per_source, uint32_t windows, uint32_t cap, uint32_t window_log2) {
+    PB_REQUIRE(b && stage_dev && cursors_dev, "NULL argument");
+    PB_REQUIRE(n_sources >= 1 && windows >= 1 && windows <= windows_per_source, "need 1 <= windows <= windows_per_source");
+    PB_REQUIRE(window_log2 >= 5 && window_log2 <= 31 && (cap & 3u) == 0, "bad window_log2 / cap");
+    PB_REQUIRE(((uint64_t)(windows - 1) << window_log2) < (b->hi_bit - b->lo_bit), "windows reach past this shard");
+    PB_REQUIRE((b->lo_bit & ((1ull << window_log2) - 1)) == 0, "the shard must start on a window boundary");
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
+    launch_begin(ctx);
+    bloom_apply_sources<<<windows * cpw, 256, 0, ctx->stream>>>(b->words, stage_dev, cursors_dev, n_sources, windows_per_source,
+                                                                cap, window_log2, cpw);
+    return check_launch(ctx, "bloom_apply_windows");
 }
 
 int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n) {

@@ -37,7 +37,21 @@ struct Part2Dev {
     uint32_t n_windows;
     uint32_t k;
     uint32_t recip_fits32;   // m > 2^32
+    // multi-GPU routing: the bitmap of most windows lives on another GPU, so an index that does not fit its
+    // window list cannot fall back to a local RED; it goes to this list of global bit indices instead
+    uint64_t *ovf_list;
+    unsigned long long *ovf_count;
+    uint64_t ovf_cap;
 };
+
+__device__ __forceinline__ void part_overflow(const Part2Dev &p, uint64_t idx) {
+    if (p.ovf_list) {
+        const unsigned long long pos = atomicAdd(p.ovf_count, 1ull);
+        if (pos < p.ovf_cap) p.ovf_list[pos] = idx;
+    } else {
+        atomicOr(p.words + (idx >> 5), 1u << (uint32_t)(idx & 31));
+    }
+}
 
 // exact h % m with R = floor(2^64/m) < 2^32 (m > 2^32): q = floor(h*R / 2^64) is floor(h/m) or one less
 __device__ __forceinline__ uint64_t mod_big(uint64_t h, uint64_t m, uint32_t r32) {
@@ -130,8 +144,7 @@ __global__ void __launch_bounds__(256, 4) bloom_part2_fixed16(const uint4 *__res
                     if (pos < p.cap) {
                         __stcs(p.stage + (w * p.cap + pos), loc[s]);
                     } else {  // window list full (skewed keys): straight to the bitmap
-                        const uint64_t idx = ((uint64_t)w << p.window_log2) | loc[s];
-                        atomicOr(p.words + (idx >> 5), 1u << (uint32_t)(idx & 31));
+                        part_overflow(p, ((uint64_t)w << p.window_log2) | loc[s]);
                     }
                 }
             }
@@ -263,8 +276,7 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
             if (pos < p.cap) {
                 __stcs(p.stage + (w * p.cap + pos), v);
             } else {
-                const uint64_t idx = ((uint64_t)w << p.window_log2) | v;
-                atomicOr(p.words + (idx >> 5), 1u << (uint32_t)(idx & 31));
+                part_overflow(p, ((uint64_t)w << p.window_log2) | v);
             }
         }
         pp ^= 1;
@@ -297,6 +309,38 @@ __global__ void __launch_bounds__(256) bloom_apply2(Part2Dev p, uint32_t ctas_pe
         for (uint32_t i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) {
             const uint32_t v = list[i];
             if (v != kSentinel) atomicOr(words + (v >> 5), 1u << (v & 31));
+        }
+    }
+}
+
+// pass 2 on a range shard (multi-GPU): window w of this shard receives one list per source rank,
+// laid out [source][w][cap] with counts [source][w] -- exactly what the all-to-all of the per-rank stagings
+// delivers.
+__global__ void __launch_bounds__(256) bloom_apply_sources(uint32_t *__restrict__ shard_words, const uint32_t *__restrict__ stage,
+                                                           const unsigned int *__restrict__ cursors, uint32_t n_sources,
+                                                           uint32_t wps, uint32_t cap, uint32_t window_log2,
+                                                           uint32_t ctas_per_window) {
+    const uint32_t w = blockIdx.x / ctas_per_window;
+    const uint32_t c = blockIdx.x % ctas_per_window;
+    uint32_t *words = shard_words + ((uint64_t)w << (window_log2 - 5));
+    for (uint32_t s = 0; s < n_sources; ++s) {
+        uint32_t cnt = cursors[s * wps + w];
+        if (cnt > cap) cnt = cap;
+        const uint32_t *list = stage + (uint64_t)(s * wps + w) * cap;
+        const uint32_t n4 = cnt >> 2;
+        const uint4 *list4 = reinterpret_cast<const uint4 *>(list);
+        for (uint32_t i = c * blockDim.x + threadIdx.x; i < n4; i += ctas_per_window * blockDim.x) {
+            const uint4 v = __ldcs(list4 + i);
+            if (v.x != kSentinel) atomicOr(words + (v.x >> 5), 1u << (v.x & 31));
+            if (v.y != kSentinel) atomicOr(words + (v.y >> 5), 1u << (v.y & 31));
+            if (v.z != kSentinel) atomicOr(words + (v.z >> 5), 1u << (v.z & 31));
+            if (v.w != kSentinel) atomicOr(words + (v.w >> 5), 1u << (v.w & 31));
+        }
+        if (c == 0) {
+            for (uint32_t i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) {
+                const uint32_t v = list[i];
+                if (v != kSentinel) atomicOr(words + (v >> 5), 1u << (v & 31));
+            }
         }
     }
 }

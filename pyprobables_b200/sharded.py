@@ -32,19 +32,40 @@ from .keys import pack_keys
 
 @dataclass(frozen=True)
 class ShardPlan:
-    """who owns which bits of an m-bit filter split over `world` ranks"""
+    """who owns which bits of an m-bit filter split over `world` ranks.  Shards are whole *windows* of
+    2^window_log2 bits (the unit the partitioned insert bins bit indices by), so a window never straddles
+    two GPUs: rank g owns windows [g*windows_per_rank, (g+1)*windows_per_rank)."""
 
     num_bits: int
     world: int
     shard_bits: int
+    window_log2: int = 5
+    windows_per_rank: int = 0
+
+    MAX_WINDOWS = 512  # kMaxWindows2 in csrc/pb_bloom_part.cuh
 
     @staticmethod
-    def make(num_bits: int, world: int) -> "ShardPlan":
+    def make(num_bits: int, world: int, window_log2: int = 27) -> "ShardPlan":
         if world < 1 or num_bits < 1:
             raise ValueError("world and num_bits must be >= 1")
-        s = -(-num_bits // world)
-        s = (s + 31) // 32 * 32
-        return ShardPlan(int(num_bits), int(world), int(s))
+        wl = max(10, min(int(window_log2), 31))
+        nwin = lambda w: -(-num_bits // (1 << w))
+        while wl > 10 and nwin(wl) < 4 * world:  # small filters: a few windows per rank keeps the split even
+            wl -= 1
+        while wl < 31 and -(-nwin(wl) // world) * world > ShardPlan.MAX_WINDOWS:
+            wl += 1
+        wps = -(-nwin(wl) // world)
+        if wps * world > ShardPlan.MAX_WINDOWS:
+            raise ValueError("filter too large for the windowed shard plan")
+        return ShardPlan(int(num_bits), int(world), int(wps << wl), int(wl), int(wps))
+
+    @property
+    def total_windows(self) -> int:
+        return self.windows_per_rank * self.world
+
+    def active_windows(self, rank: int) -> int:
+        lo, hi = self.bounds(rank)
+        return -(-(hi - lo) // (1 << self.window_log2))
 
     def bounds(self, rank: int) -> tuple[int, int]:
         lo = min(rank * self.shard_bits, self.num_bits)
@@ -131,7 +152,7 @@ class ShardedBloomFilter:
     resident uint8[n,16] tensors or anything pack_keys accepts)."""
 
     def __init__(self, est_elements, false_positive_rate, group=None, device=None, context=None, chunk_keys: int = 1 << 25,
-                 mode: str = "route"):
+                 mode: str = "fused"):
         import torch
         import torch.distributed as dist
 
@@ -149,8 +170,8 @@ class ShardedBloomFilter:
         # run on torch's current stream so kernels, NCCL collectives and tensor ops are ordered without
         # host synchronization (handle 0 is the legacy default stream = cudaStreamLegacy, 0x1)
         self._ctx = context if context is not None else torch_stream_context(self.device)
-        if mode not in ("route", "gather"):
-            raise ValueError("mode must be 'route' or 'gather'")
+        if mode not in ("fused", "route", "gather"):
+            raise ValueError("mode must be 'fused', 'route' or 'gather'")
         self.mode = mode
         self.chunk_keys = int(chunk_keys)
         h = C.c_void_p()
@@ -160,6 +181,7 @@ class ShardedBloomFilter:
         self._els_added = 0
         self._send = None
         self._counts = None
+        self._fused_bufs = None
 
     # -- properties in the reference's vocabulary
     @property
@@ -215,12 +237,12 @@ class ShardedBloomFilter:
         return n.value
 
     # -- hot path
-    def _ensure_buffers(self, chunk: int):
+    def _ensure_buffers(self, chunk: int, worst_case: bool = False):
         torch = self._torch
-        # every owner can receive all k indices of a chunk in the worst case; size slots for the uniform
-        # expectation with generous slack and fall back to smaller chunks on overflow
+        # every owner can receive all k indices of a chunk in the worst case; slots are sized for the uniform
+        # expectation with generous slack unless worst_case asks for the full bound
         slot = int(chunk * self._k / self.world * 1.25) + 4096
-        if self.world == 1:
+        if self.world == 1 or worst_case:
             slot = chunk * self._k
         if self._send is None or self._send.numel() < slot * self.world:
             self._send = torch.empty(slot * self.world, dtype=torch.int64, device=f"cuda:{self.device}")
@@ -248,19 +270,28 @@ class ShardedBloomFilter:
             self._els_added += n
             return
         if t.shape[1] != 16:
-            raise TypeError("route mode takes 16-byte keys; use mode='gather' for other widths")
-        stream = torch.cuda.current_stream(self.device)
-        # all ranks walk the same number of chunks
-        n_chunks = torch.tensor([-(-n // self.chunk_keys)], dtype=torch.int64, device=t.device)
-        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)
+            raise TypeError("fused/route modes take 16-byte keys; use mode='gather' for other widths")
+        if self.mode == "fused":
+            self._add_fused(t)
+            self._els_added += n
+            return
+        self._add_route(t, self.chunk_keys, worst_case=False)
+        self._els_added += n
+
+    def _add_route(self, t, chunk_keys: int, worst_case: bool) -> None:
+        """u64 global indices binned by owner + all-to-all-v with counts + RED apply.  worst_case sizes every
+        owner's slot for ALL indices of a chunk, which makes the path exact for any key distribution."""
+        torch, dist = self._torch, self._dist
+        n = int(t.shape[0])
+        n_chunks = torch.tensor([-(-n // chunk_keys)], dtype=torch.int64, device=t.device)
+        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)  # all ranks walk the same number of chunks
         for ci in range(int(n_chunks.item())):
-            lo = min(ci * self.chunk_keys, n)
-            hi = min(lo + self.chunk_keys, n)
-            self._ensure_buffers(max(hi - lo, 1))
+            lo = min(ci * chunk_keys, n)
+            hi = min(lo + chunk_keys, n)
+            self._ensure_buffers(max(hi - lo, 1), worst_case)
             self._counts.zero_()
             if hi > lo:
-                part = t[lo:hi]
-                kb = pack_keys(part)
+                kb = pack_keys(t[lo:hi])
                 _native.call("pb_bloom_route_keys", self._ctx.handle, kb.ref(), self._m, self._k, self.plan.shard_bits,
                              self.world, C.c_void_p(self._send.data_ptr()), self._slot, C.c_void_p(self._counts.data_ptr()))
             counts = self._counts[: self.world].clone()
@@ -272,7 +303,77 @@ class ShardedBloomFilter:
             recv, _ = exchange_indices(segs, recv_counts.tolist(), self.group)
             if recv.numel() and self._h is not None:
                 _native.call("pb_bloom_add_bit_indices", self._h, C.c_void_p(recv.data_ptr()), recv.numel())
-        self._els_added += n
+
+    # -- fused route + partition (default): see pb_bloom_partition_keys in include/pb200.h
+    def _fused_buffers(self, chunk: int):
+        torch = self._torch
+        plan = self.plan
+        if self._fused_bufs is not None and self._fused_bufs["chunk"] >= chunk:
+            return self._fused_bufs
+        slack = C.c_uint64()
+        _native.call("pb_bloom_partition_slack", self._ctx.handle, chunk, C.byref(slack))
+        expect = chunk * self._k * (1 << plan.window_log2) / self._m
+        cap = int(expect * 1.03 + 6.0 * math.sqrt(expect + 1.0)) + slack.value
+        cap = (cap + 3) // 4 * 4
+        W = plan.total_windows
+        if cap * W > 0xFFFFFFF0:
+            raise ValueError("chunk_keys too large for the staging layout; lower chunk_keys")
+        dev = f"cuda:{self.device}"
+        b = {"chunk": chunk, "cap": cap,
+             "send": torch.empty(W * cap, dtype=torch.int32, device=dev), "recv": torch.empty(W * cap, dtype=torch.int32, device=dev),
+             "scur": torch.zeros(W, dtype=torch.int32, device=dev), "rcur": torch.zeros(W, dtype=torch.int32, device=dev),
+             "ovf": torch.empty(1 << 22, dtype=torch.int64, device=dev), "ovf_n": torch.zeros(1, dtype=torch.int64, device=dev)}
+        self._fused_bufs = b
+        return b
+
+    def _add_fused(self, t) -> None:
+        torch, dist = self._torch, self._dist
+        plan = self.plan
+        n = int(t.shape[0])
+        n_chunks = torch.tensor([-(-n // self.chunk_keys)], dtype=torch.int64, device=t.device)
+        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)
+        n_chunks = int(n_chunks.item())
+        if n_chunks == 0:
+            return
+        b = self._fused_buffers(min(self.chunk_keys, max(n, 1)) if n_chunks == 1 else self.chunk_keys)
+        b["ovf_n"].zero_()
+        act = plan.active_windows(self.rank)
+        for ci in range(n_chunks):
+            lo = min(ci * self.chunk_keys, n)
+            hi = min(lo + self.chunk_keys, n)
+            kb = pack_keys(t[lo:hi]) if hi > lo else pack_keys(t[:0])
+            _native.call("pb_bloom_partition_keys", self._ctx.handle, kb.ref(), self._m, self._k, plan.window_log2, plan.total_windows,
+                         b["cap"], C.c_void_p(b["send"].data_ptr()), C.c_void_p(b["scur"].data_ptr()),
+                         C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
+            dist.all_to_all_single(b["rcur"], b["scur"], group=self.group)
+            dist.all_to_all_single(b["recv"], b["send"], group=self.group)
+            if self._h is not None and act > 0:
+                _native.call("pb_bloom_apply_window_lists", self._h, C.c_void_p(b["recv"].data_ptr()), C.c_void_p(b["rcur"].data_ptr()),
+                             self.world, plan.windows_per_rank, act, b["cap"], plan.window_log2)
+        # indices that did not fit their window list (heavily duplicated keys): exact slow path, all ranks together
+        worst = b["ovf_n"].clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
+        worst = int(worst.item())
+        if worst > b["ovf"].numel():
+            # more strays than the list holds (e.g. one key repeated millions of times): OR is idempotent, so
+            # simply run the whole batch again through the exact u64 route with worst-case slots
+            self._add_route(t, min(self.chunk_keys, 1 << 20), worst_case=True)
+        elif worst > 0:
+            self._route_indices(b["ovf"][: int(b["ovf_n"].item())])
+
+    def _route_indices(self, idx) -> None:
+        """send global bit indices (int64 tensor) to their owners and OR them in (collective)"""
+        torch = self._torch
+        owner = torch.div(idx, self.plan.shard_bits, rounding_mode="floor")
+        order = torch.argsort(owner)
+        idx = idx[order].contiguous()
+        counts = torch.bincount(owner, minlength=self.world)[: self.world]
+        recv_counts = exchange_counts(counts, self.group)
+        offs = [0] + torch.cumsum(counts, 0).tolist()
+        segs = [idx[offs[d] : offs[d + 1]] for d in range(self.world)]
+        recv, _ = exchange_indices(segs, recv_counts.tolist(), self.group)
+        if recv.numel() and self._h is not None:
+            _native.call("pb_bloom_add_bit_indices", self._h, C.c_void_p(recv.data_ptr()), recv.numel())
 
     def _add_gather(self, t) -> None:
         torch, dist = self._torch, self._dist
