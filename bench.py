@@ -278,9 +278,11 @@ def run_ours(args) -> None:
         for _ in range(max(args.warmup, 0)):
             step()
         barrier()
-        ctx.set_option("kernel_timing", 1)
-        ctx.kernel_times()
-        launches0 = ctx.launch_count
+        ctxs = [ctx] + ([filt._ctx_part] if getattr(filt, "_ctx_part", None) is not None else [])
+        for c in ctxs:
+            c.set_option("kernel_timing", 1)
+            c.kernel_times()
+        launches0 = sum(c.launch_count for c in ctxs)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -293,9 +295,13 @@ def run_ours(args) -> None:
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else {}
-        launches = ctx.launch_count - launches0
-        ktimes = ctx.kernel_times()
-        ctx.set_option("kernel_timing", 0)
+        launches = sum(c.launch_count for c in ctxs) - launches0
+        ktimes = {}
+        for c in ctxs:
+            for kn, (cnt, tot) in c.kernel_times().items():
+                old = ktimes.get(kn, (0, 0.0))
+                ktimes[kn] = (old[0] + cnt, old[1] + tot)
+            c.set_option("kernel_timing", 0)
         if dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -417,7 +423,7 @@ def main() -> None:
     ap.add_argument("--keys", type=int, default=10**9, help="keys per GPU per step")
     ap.add_argument("--e2e-keys", type=int, default=1 << 27)
     ap.add_argument("--ref-keys", type=int, default=100_000, help="keys per step of the pure-Python reference arm")
-    ap.add_argument("--chunk-keys", type=int, default=1 << 25)
+    ap.add_argument("--chunk-keys", type=int, default=1 << 26)
     ap.add_argument("--shard-mode", default="fused", choices=["fused", "route", "gather"])
     ap.add_argument("--insert-mode", type=int, default=0, help="bloom_insert_mode: 0 auto, 1 direct RED, 2 partitioned")
     ap.add_argument("--window-log2", type=int, default=0, help="bloom_window_log2_bits override")

@@ -142,7 +142,7 @@ int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uin
 int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
                             uint32_t n_windows, uint32_t cap, uint32_t *stage_dev, uint32_t *cursors_dev,
                             uint64_t *ovf_list_dev, uint64_t ovf_cap, uint64_t *ovf_count_dev);
-int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint64_t *out_entries);
+int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint32_t n_windows, uint64_t *out_entries);
 int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const uint32_t *cursors_dev, uint32_t n_sources,
                                 uint32_t windows_per_source, uint32_t windows, uint32_t cap, uint32_t window_log2);
 /* apply global bit indices that fall into this shard's [lo, hi) (others are an error count) */

@@ -107,7 +107,7 @@ SIGNATURES: dict[str, list] = {
     "pb_bloom_create_shard": [_vp, _u64, _u32, _u64, _u64, _P(_vp)],
     "pb_bloom_route_keys": [_vp, _KP, _u64, _u32, _u64, _u32, _vp, _u64, _vp],
     "pb_bloom_partition_keys": [_vp, _KP, _u64, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u64, _vp],
-    "pb_bloom_partition_slack": [_vp, _u64, _P(_u64)],
+    "pb_bloom_partition_slack": [_vp, _u64, _u32, _u32, _P(_u64)],
     "pb_bloom_apply_window_lists": [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32],
     "pb_bloom_add_bit_indices": [_vp, _vp, _u64],
     "pb_bloom_test_bit_indices": [_vp, _vp, _u64, _vp],

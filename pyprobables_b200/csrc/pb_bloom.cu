@@ -366,6 +366,15 @@ static int launch_check(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd, uint
         default: st = CALL(8); break;       \
     }
 
+// Quota (list entries a CTA reserves per window at a time) for a pass-1 launch of n keys: about 1/16 of what
+// one CTA expects to write to one window, so the sentinels left in partly used quotas stay a few percent.
+static uint32_t pick_quota(uint64_t n, uint32_t k, uint32_t n_windows, int grid) {
+    const double per = (double)n * k / ((double)n_windows * (double)std::max(grid, 1));
+    uint32_t q = 32;
+    while (q < kQuota && (double)q * 16.0 < per) q <<= 1;
+    return q;
+}
+
 struct PartPlan {
     bool use = false;
     uint32_t window_log2 = 0;
@@ -375,6 +384,7 @@ struct PartPlan {
     int kg = 0, ng = 0;
     int version = 3;  // 1: bloom_part_fixed16 + bloom_apply_windows, 2/3: pb_bloom_part.cuh
     int halves = 1;   // 2: the staging is split in two so pass 2 of one chunk overlaps pass 1 of the next
+    uint32_t quota = kQuota;
     int grid = 0;     // CTAs of the pass-1 launch (the v2 staging slack depends on it)
 };
 
@@ -419,6 +429,7 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     if (version >= 2) chunk = std::min<uint64_t>(chunk, (0xF0000000ull - (uint64_t)grid * kQuota) / b->k);  // u32 cursors
     if (halves == 2) chunk = std::min<uint64_t>(chunk, (n + 3) / 4);  // at least four chunks to pipeline
     pl.halves = halves;
+    pl.quota = pick_quota(chunk, b->k, (uint32_t)nw, grid);  // <= kQuota, which the slack above allowed for
     if (chunk < 1024) return pl;
     pl.version = version;
     pl.grid = grid;
@@ -476,6 +487,7 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
         pd.n_windows = pl.n_windows;
         pd.k = b->k;
         pd.recip_fits32 = b->num_bits > (1ull << 32) ? 1u : 0u;
+        pd.quota = pl.quota;
         pd.ovf_list = nullptr;
         pd.ovf_count = nullptr;
         pd.ovf_cap = 0;
@@ -836,6 +848,7 @@ int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits,
     pd.n_windows = n_windows;
     pd.k = k;
     pd.recip_fits32 = num_bits > (1ull << 32) ? 1u : 0u;
+    pd.quota = pick_quota(keys->n, k, n_windows, grid_for(ctx, keys->n, 256, 4));
     pd.ovf_list = ovf_list_dev;
     pd.ovf_count = (unsigned long long *)ovf_count_dev;
     pd.ovf_cap = ovf_cap;
@@ -865,9 +878,11 @@ int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits,
 
 // Slack a window list needs beyond its expected share for a pb_bloom_partition_keys call of n keys
 // (partly used quotas of every CTA of the launch); callers size `cap` with it.
-int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint64_t *out_entries) {
-    PB_REQUIRE(ctx && out_entries, "NULL argument");
-    *out_entries = (uint64_t)grid_for(ctx, n_keys, 256, 4) * kQuota + 8192;
+int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint32_t n_windows, uint64_t *out_entries) {
+    PB_REQUIRE(ctx && out_entries && k >= 1 && n_windows >= 1, "bad argument");
+    // every CTA of the launch can leave one partly used quota per window
+    const int grid = grid_for(ctx, n_keys, 256, 4);
+    *out_entries = (uint64_t)grid * pick_quota(n_keys, k, n_windows, grid) + 8192;
     return PB_OK;
 }
 
@@ -883,7 +898,9 @@ int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const ui
     PB_REQUIRE((b->lo_bit & ((1ull << window_log2) - 1)) == 0, "the shard must start on a window boundary");
     pb_ctx *ctx = b->ctx;
     DeviceGuard g(ctx->device);
-    const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
+    // windows of 32 MiB and more: one window in flight (every resident CTA slot works on it) or L2 thrashes
+    const int64_t per_sm = window_log2 >= 28 ? std::max<int64_t>(ctx->bloom_apply_cpw_per_sm, 8) : ctx->bloom_apply_cpw_per_sm;
+    const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(per_sm, 32));
     launch_begin(ctx);
     bloom_apply_sources<<<windows * cpw, 256, 0, ctx->stream>>>(b->words, stage_dev, cursors_dev, n_sources, windows_per_source,
                                                                 cap, window_log2, cpw);

@@ -23,7 +23,7 @@
 namespace pb {
 
 constexpr uint32_t kSentinel = 0xFFFFFFFFu;  // never a valid window-local bit index (windows are <= 2^31 bits)
-constexpr uint32_t kQuota = 1024;            // list entries a CTA reserves per window and refill
+constexpr uint32_t kQuota = 1024;            // most list entries a CTA reserves per window and refill (Part2Dev.quota)
 constexpr int kMaxWindows2 = 512;
 
 struct Part2Dev {
@@ -37,6 +37,7 @@ struct Part2Dev {
     uint32_t n_windows;
     uint32_t k;
     uint32_t recip_fits32;   // m > 2^32
+    uint32_t quota;          // list entries a CTA reserves per window and refill (<= kQuota)
     // multi-GPU routing: the bitmap of most windows lives on another GPU, so an index that does not fit its
     // window list cannot fall back to a local RED; it goes to this list of global bit indices instead
     uint64_t *ovf_list;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256, 4) bloom_part2_fixed16(const uint4 *__res
                     // hand back what is left of the old quota as sentinels, then reserve a new one
                     const uint32_t stop = e < p.cap ? e : p.cap;
                     for (uint32_t q = c; q < stop; ++q) p.stage[w * p.cap + q] = kSentinel;
-                    const uint32_t take = need > kQuota ? need : kQuota;
+                    const uint32_t take = need > p.quota ? need : p.quota;
                     c = atomicAdd(p.cursors + w, take);
                     lim[w] = c + take;
                 }
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
                     if (c + need > e) {
                         const uint32_t stop = e < p.cap ? e : p.cap;
                         for (uint32_t q = c; q < stop; ++q) p.stage[w * p.cap + q] = kSentinel;
-                        const uint32_t take = need > kQuota ? need : kQuota;
+                        const uint32_t take = need > p.quota ? need : p.quota;
                         c = atomicAdd(p.cursors + w, take);
                         lim[w] = c + take;
                     }

@@ -151,7 +151,7 @@ class ShardedBloomFilter:
     Every rank constructs it with the same arguments; `add_many` takes each rank's own keys (device
     resident uint8[n,16] tensors or anything pack_keys accepts)."""
 
-    def __init__(self, est_elements, false_positive_rate, group=None, device=None, context=None, chunk_keys: int = 1 << 25,
+    def __init__(self, est_elements, false_positive_rate, group=None, device=None, context=None, chunk_keys: int = 1 << 26,
                  mode: str = "fused"):
         import torch
         import torch.distributed as dist
@@ -182,6 +182,7 @@ class ShardedBloomFilter:
         self._send = None
         self._counts = None
         self._fused_bufs = None
+        self._s_part = self._s_comm = self._ctx_part = None
 
     # -- properties in the reference's vocabulary
     @property
@@ -310,23 +311,36 @@ class ShardedBloomFilter:
         plan = self.plan
         if self._fused_bufs is not None and self._fused_bufs["chunk"] >= chunk:
             return self._fused_bufs
+        W = plan.total_windows
         slack = C.c_uint64()
-        _native.call("pb_bloom_partition_slack", self._ctx.handle, chunk, C.byref(slack))
+        _native.call("pb_bloom_partition_slack", self._ctx.handle, chunk, self._k, W, C.byref(slack))
         expect = chunk * self._k * (1 << plan.window_log2) / self._m
         cap = int(expect * 1.03 + 6.0 * math.sqrt(expect + 1.0)) + slack.value
         cap = (cap + 3) // 4 * 4
-        W = plan.total_windows
         if cap * W > 0xFFFFFFF0:
             raise ValueError("chunk_keys too large for the staging layout; lower chunk_keys")
         dev = f"cuda:{self.device}"
+        i32 = torch.int32
         b = {"chunk": chunk, "cap": cap,
-             "send": torch.empty(W * cap, dtype=torch.int32, device=dev), "recv": torch.empty(W * cap, dtype=torch.int32, device=dev),
-             "scur": torch.zeros(W, dtype=torch.int32, device=dev), "rcur": torch.zeros(W, dtype=torch.int32, device=dev),
-             "ovf": torch.empty(1 << 22, dtype=torch.int64, device=dev), "ovf_n": torch.zeros(1, dtype=torch.int64, device=dev)}
+             # two halves of everything: pass 1 of chunk c+1, the all-to-all of chunk c and pass 2 of chunk c-1 overlap
+             "send": [torch.empty(W * cap, dtype=i32, device=dev) for _ in range(2)],
+             "recv": [torch.empty(W * cap, dtype=i32, device=dev) for _ in range(2)],
+             "scur": [torch.zeros(W, dtype=i32, device=dev) for _ in range(2)],
+             "rcur": [torch.zeros(W, dtype=i32, device=dev) for _ in range(2)],
+             "ovf": torch.empty(1 << 22, dtype=torch.int64, device=dev), "ovf_n": torch.zeros(1, dtype=torch.int64, device=dev),
+             "ev_part": [torch.cuda.Event() for _ in range(2)], "ev_comm": [torch.cuda.Event() for _ in range(2)],
+             "ev_apply": [torch.cuda.Event() for _ in range(2)]}
+        if self._s_part is None:
+            self._s_part = torch.cuda.Stream(device=self.device)
+            self._s_comm = torch.cuda.Stream(device=self.device)
+            self._ctx_part = _native.Context(self.device, stream=self._s_part.cuda_stream)
         self._fused_bufs = b
         return b
 
     def _add_fused(self, t) -> None:
+        """three-stage pipeline over chunks of keys, one CUDA stream per stage:
+             pass 1 (hash + bin by global window)  ->  NCCL all-to-all of the window lists  ->  pass 2 (RED.OR into my shard)
+        Pass 2 runs on the stream the filter was created on, so everything the caller does next is ordered after it."""
         torch, dist = self._torch, self._dist
         plan = self.plan
         n = int(t.shape[0])
@@ -336,20 +350,37 @@ class ShardedBloomFilter:
         if n_chunks == 0:
             return
         b = self._fused_buffers(min(self.chunk_keys, max(n, 1)) if n_chunks == 1 else self.chunk_keys)
+        main = torch.cuda.current_stream(self.device)
         b["ovf_n"].zero_()
+        self._s_part.wait_stream(main)  # keys and the zeroed overflow counter are ready
+        self._s_comm.wait_stream(main)
         act = plan.active_windows(self.rank)
         for ci in range(n_chunks):
+            h = ci & 1
             lo = min(ci * self.chunk_keys, n)
             hi = min(lo + self.chunk_keys, n)
             kb = pack_keys(t[lo:hi]) if hi > lo else pack_keys(t[:0])
-            _native.call("pb_bloom_partition_keys", self._ctx.handle, kb.ref(), self._m, self._k, plan.window_log2, plan.total_windows,
-                         b["cap"], C.c_void_p(b["send"].data_ptr()), C.c_void_p(b["scur"].data_ptr()),
-                         C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
-            dist.all_to_all_single(b["rcur"], b["scur"], group=self.group)
-            dist.all_to_all_single(b["recv"], b["send"], group=self.group)
+            with torch.cuda.stream(self._s_part):
+                if ci >= 2:
+                    self._s_part.wait_event(b["ev_comm"][h])  # the all-to-all that read this send half is done
+                _native.call("pb_bloom_partition_keys", self._ctx_part.handle, kb.ref(), self._m, self._k, plan.window_log2,
+                             plan.total_windows, b["cap"], C.c_void_p(b["send"][h].data_ptr()), C.c_void_p(b["scur"][h].data_ptr()),
+                             C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
+                b["ev_part"][h].record(self._s_part)
+            with torch.cuda.stream(self._s_comm):
+                self._s_comm.wait_event(b["ev_part"][h])
+                if ci >= 2:
+                    self._s_comm.wait_event(b["ev_apply"][h])  # pass 2 that read this receive half is done
+                dist.all_to_all_single(b["rcur"][h], b["scur"][h], group=self.group)
+                dist.all_to_all_single(b["recv"][h], b["send"][h], group=self.group)
+                b["ev_comm"][h].record(self._s_comm)
+            main.wait_event(b["ev_comm"][h])
             if self._h is not None and act > 0:
-                _native.call("pb_bloom_apply_window_lists", self._h, C.c_void_p(b["recv"].data_ptr()), C.c_void_p(b["rcur"].data_ptr()),
-                             self.world, plan.windows_per_rank, act, b["cap"], plan.window_log2)
+                _native.call("pb_bloom_apply_window_lists", self._h, C.c_void_p(b["recv"][h].data_ptr()),
+                             C.c_void_p(b["rcur"][h].data_ptr()), self.world, plan.windows_per_rank, act, b["cap"], plan.window_log2)
+            b["ev_apply"][h].record(main)
+        main.wait_stream(self._s_part)
+        main.wait_stream(self._s_comm)
         # indices that did not fit their window list (heavily duplicated keys): exact slow path, all ranks together
         worst = b["ovf_n"].clone()
         dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
