@@ -335,8 +335,19 @@ def run_ours(args) -> None:
             design_per_key = 16 + 8 * k + 2.0 * bitmap_bytes * n_chunks / n_keys if "bloom_part" in ktimes else algo_per_key
             avg_ms = tot_ms / max(n_launch, 1)
             achieved = keys_per_launch * algo_per_key / (avg_ms * 1e-3) / 1e9
+            traffic, traffic_src = None, None
+            try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (scaled to this launch size)
+                tj = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+                tk = tj.get(name)
+                if tk:
+                    per_key = (tk["dram_bytes_read"] + tk["dram_bytes_write"]) / tk.get("keys_per_launch", tj["keys_per_launch"])
+                    traffic = per_key * keys_per_launch
+                    traffic_src = f"profiles/r1_traffic.json ({tk['kernel']}): {per_key:.1f} DRAM B/key x {keys_per_launch:.0f} keys per launch"
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": keys_per_launch * algo_per_key,
                     "algorithmic_bytes_per_key": algo_per_key, "keys_per_launch": keys_per_launch,
                     "launches": n_launch, "avg_launch_ms": avg_ms, "kernel_share_of_step": tot_ms / ms,
                     "kernels": {kn: {"launches": v[0], "total_ms": v[1]} for kn, v in ktimes.items()},

@@ -86,11 +86,21 @@ __global__ void __launch_bounds__(256)
             uint64_t h[KG];
             fnv_group_16<KG>(w, s0, h);
             uint32_t bit[KG];
-            // issue all probes of the group before combining them: k independent sector reads in flight
+            // Probes of a phase are issued together (independent sector reads in flight).  The reference stops at
+            // the first zero bit (bloom.py:268-271); two phases keep most of that saving for absent keys -- at 50 %
+            // fill 7 of 8 absent keys end after the first three probes -- without serialising present keys.
+            constexpr int kFirst = KG < 3 ? KG : 3;
 #pragma unroll
-            for (int j = 0; j < KG; ++j) bit[j] = (s0 + j < b.k) ? bloom_test(b, h[j]) : 1u;
+            for (int j = 0; j < kFirst; ++j) bit[j] = (s0 + j < b.k) ? bloom_test(b, h[j]) : 1u;
 #pragma unroll
-            for (int j = 0; j < KG; ++j) ok &= bit[j];
+            for (int j = 0; j < kFirst; ++j) ok &= bit[j];
+            if (ok) {
+#pragma unroll
+                for (int j = kFirst; j < KG; ++j) bit[j] = (s0 + j < b.k) ? bloom_test(b, h[j]) : 1u;
+#pragma unroll
+                for (int j = kFirst; j < KG; ++j) ok &= bit[j];
+            }
+            if (!ok) break;
         }
         out[i] = (uint8_t)ok;
     }
