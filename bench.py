@@ -435,7 +435,7 @@ def main() -> None:
     ap.add_argument("--e2e-keys", type=int, default=1 << 27)
     ap.add_argument("--ref-keys", type=int, default=100_000, help="keys per step of the pure-Python reference arm")
     ap.add_argument("--chunk-keys", type=int, default=1 << 26)
-    ap.add_argument("--shard-mode", default="fused", choices=["fused", "route", "gather"])
+    ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "p2p_direct", "fused", "route", "gather"])
     ap.add_argument("--insert-mode", type=int, default=0, help="bloom_insert_mode: 0 auto, 1 direct RED, 2 partitioned")
     ap.add_argument("--window-log2", type=int, default=0, help="bloom_window_log2_bits override")
     ap.add_argument("--no-e2e", action="store_true")

@@ -43,12 +43,12 @@ def main():
     dkeys = torch.from_numpy(host_keys).cuda()
     all_keys = orc.pack(orc.uniform_keys(0, total))
     skew = torch.from_numpy(np.repeat(orc.uniform_keys(5 * 10**9 + rank, 1), 2_100_000, axis=0)).cuda()  # overflows its windows
-    for mode in ("fused", "route", "gather"):
+    for mode in ("p2p", "p2p_direct", "fused", "route", "gather"):
         f = ShardedBloomFilter(a.est, 0.01, mode=mode, chunk_keys=700_000)
         f.add_many(dkeys)
         ob = orc.Bloom(f.number_bits, f.number_hashes)
         ob.add(all_keys)
-        if mode == "fused":  # a heavily duplicated batch must take the exact overflow path
+        if mode in ("fused", "p2p", "p2p_direct"):  # a heavily duplicated batch must take the exact overflow path
             f.add_many(skew)
             for r in range(world):
                 ob.add(orc.pack(orc.uniform_keys(5 * 10**9 + r, 1)))

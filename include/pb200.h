@@ -145,6 +145,25 @@ int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits,
 int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint32_t n_windows, uint64_t *out_entries);
 int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const uint32_t *cursors_dev, uint32_t n_sources,
                                 uint32_t windows_per_source, uint32_t windows, uint32_t cap, uint32_t window_log2);
+/* The same insert as ONE fused compute + exchange kernel over NVLink peer memory (no NCCL on the data path):
+ * every rank owns a mailbox (window lists per source rank, double buffered) that all peers map through CUDA
+ * IPC; pb_p2p_partition_send hashes a chunk of keys and stores each bit index straight into the list of its
+ * window inside the OWNER's mailbox, then publishes the list lengths and raises per-source flags;
+ * pb_p2p_apply on the owner waits for all sources' flags, ORs the lists into its shard and raises the flags that
+ * let the sources reuse that half.  Both calls are stream-ordered and never synchronise the host; every rank
+ * must call them the same number of times.  handles: world x 64 bytes from pb_p2p_export of every rank. */
+typedef struct pb_p2p pb_p2p;
+int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t windows_per_rank, uint32_t cap, pb_p2p **out);
+/* exchange variant, before the first chunk: 0 (default) = pass 1 fills a local staging and the copy engines
+ * push each destination's block over NVLink (SMs stay with the compute passes); 1 = pass 1 stores every entry
+ * straight into the owner's mailbox (SM stores over NVLink, no staging) */
+int pb_p2p_set_direct(pb_p2p *p, int direct_stores);
+int pb_p2p_export(pb_p2p *p, uint8_t *handle_out /* 64 bytes */);
+int pb_p2p_connect(pb_p2p *p, const uint8_t *handles /* world * 64 bytes */);
+int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
+                          uint64_t *ovf_list_dev, uint64_t ovf_cap, uint64_t *ovf_count_dev);
+int pb_p2p_apply(pb_p2p *p, pb_bloom *shard, uint32_t active_windows, uint32_t window_log2);
+int pb_p2p_destroy(pb_p2p *p);
 /* apply global bit indices that fall into this shard's [lo, hi) (others are an error count) */
 int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n);
 int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, uint8_t *out_dev);

@@ -109,6 +109,13 @@ SIGNATURES: dict[str, list] = {
     "pb_bloom_partition_keys": [_vp, _KP, _u64, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u64, _vp],
     "pb_bloom_partition_slack": [_vp, _u64, _u32, _u32, _P(_u64)],
     "pb_bloom_apply_window_lists": [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32],
+    "pb_p2p_create": [_vp, _u32, _u32, _u32, _u32, _P(_vp)],
+    "pb_p2p_set_direct": [_vp, _i32],
+    "pb_p2p_export": [_vp, _vp],
+    "pb_p2p_connect": [_vp, _vp],
+    "pb_p2p_partition_send": [_vp, _KP, _u64, _u32, _u32, _vp, _u64, _vp],
+    "pb_p2p_apply": [_vp, _vp, _u32, _u32],
+    "pb_p2p_destroy": [_vp],
     "pb_bloom_add_bit_indices": [_vp, _vp, _u64],
     "pb_bloom_test_bit_indices": [_vp, _vp, _u64, _vp],
     "pb_cms_create": [_vp, _u32, _u32, _P(_vp)],

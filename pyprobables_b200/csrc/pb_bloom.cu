@@ -37,6 +37,9 @@ struct pb_bloom {
 
 namespace pb {
 
+uint32_t *bloom_words(pb_bloom *b) { return b->words; }
+pb_ctx *bloom_ctx(pb_bloom *b) { return b->ctx; }
+
 struct BloomDev {
     uint32_t *words;
     FastMod fm;
@@ -511,7 +514,7 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
 #define PB_P2(KG, NG)                                                                                   \
     do {                                                                                                \
         if (pl.version == 2) bloom_part2_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd);    \
-        else bloom_part3_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd);                    \
+        else bloom_part3_fixed16<KG, NG, false><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd, P2PDst{});                    \
     } while (0)
             case 101: PB_P2(1, 1); break;
             case 102: PB_P2(2, 1); break;
@@ -867,7 +870,7 @@ int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits,
     const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
     launch_begin(ctx);
     switch (ng * 100 + kg) {
-#define PB_P3(KG, NG) bloom_part3_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, keys->n, pd)
+#define PB_P3(KG, NG) bloom_part3_fixed16<KG, NG, false><<<grid, 256, 0, ctx->stream>>>(k4, keys->n, pd, P2PDst{})
         case 101: PB_P3(1, 1); break;
         case 102: PB_P3(2, 1); break;
         case 103: PB_P3(3, 1); break;

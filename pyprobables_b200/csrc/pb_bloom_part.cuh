@@ -165,8 +165,18 @@ __global__ void __launch_bounds__(256, 4) bloom_part2_fixed16(const uint4 *__res
 // at ~45 G L2 write requests/s whatever the window count (time grew with the number of windows because the
 // requests per store instruction did); coalesced runs cut the requests by ~8x and make the cost independent
 // of the window count.
-template <int KG, int NG>
-__global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p) {
+// P2P = true: the window lists live in the receive staging of the window's OWNER GPU (peer memory mapped over
+// NVLink): pass 1 stores its entries straight into rank d's buffer, block `src_rank` of it, so the exchange step
+// of the multi-GPU insert is the kernel's own coalesced stores -- no separate all-to-all, no local staging.
+struct P2PDst {
+    uint32_t *stage[16];      // per destination rank: its receive staging [n_src][wps][cap] for this chunk's half
+    uint32_t wps;             // windows per rank
+    uint32_t src_rank;        // this GPU's block inside every destination's staging
+};
+
+template <int KG, int NG, bool P2P>
+__global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p, P2PDst dst) {
+    __shared__ uint32_t *wbase[P2P ? kMaxWindows2 : 1];  // P2P: start of window w's list in its owner's memory
     __shared__ uint32_t hist[2][kMaxWindows2];
     __shared__ uint32_t tbase[kMaxWindows2];       // window-relative list position of the tile's first entry
     __shared__ uint32_t wstart[kMaxWindows2 + 1];  // exclusive prefix sum of hist: start of the window's run in sorted[]
@@ -181,8 +191,10 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
         hist[1][w] = 0;
         cur[w] = 0;
         lim[w] = 0;
+        if (P2P) wbase[w] = dst.stage[w / dst.wps] + (size_t)(dst.src_rank * dst.wps + w % dst.wps) * p.cap;
     }
     __syncthreads();
+    auto list_of = [&](uint32_t w) -> uint32_t * { return P2P ? wbase[w] : p.stage + (size_t)w * p.cap; };
     const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
     uint32_t pp = 0;
     uint64_t tile = blockIdx.x;
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
                     const uint32_t e = lim[w];
                     if (c + need > e) {
                         const uint32_t stop = e < p.cap ? e : p.cap;
-                        for (uint32_t q = c; q < stop; ++q) p.stage[w * p.cap + q] = kSentinel;
+                        for (uint32_t q = c; q < stop; ++q) list_of(w)[q] = kSentinel;
                         const uint32_t take = need > p.quota ? need : p.quota;
                         c = atomicAdd(p.cursors + w, take);
                         lim[w] = c + take;
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
             const uint32_t pos = tbase[w] + (e - wstart[w]);
             const uint32_t v = sorted_loc[e];
             if (pos < p.cap) {
-                __stcs(p.stage + (w * p.cap + pos), v);
+                __stcs(list_of(w) + pos, v);
             } else {
                 part_overflow(p, ((uint64_t)w << p.window_log2) | v);
             }
@@ -285,12 +297,13 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
     __syncthreads();
     for (uint32_t w = tid; w < W; w += blockDim.x) {
         const uint32_t e = lim[w] < p.cap ? lim[w] : p.cap;
-        for (uint32_t q = cur[w]; q < e; ++q) p.stage[w * p.cap + q] = kSentinel;
+        for (uint32_t q = cur[w]; q < e; ++q) list_of(w)[q] = kSentinel;
     }
+    if (P2P) __threadfence_system();  // the entries must have reached the owners before the flags are raised
 }
 
 // pass 2: one window at a time (launch order); its bitmap slice stays L2 resident while its list streams by
-__global__ void __launch_bounds__(256) bloom_apply2(Part2Dev p, uint32_t ctas_per_window) {
+static __global__ void __launch_bounds__(256) bloom_apply2(Part2Dev p, uint32_t ctas_per_window) {
     const uint32_t w = blockIdx.x / ctas_per_window;
     const uint32_t c = blockIdx.x % ctas_per_window;
     uint32_t cnt = p.cursors[w];
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(256) bloom_apply2(Part2Dev p, uint32_t ctas_pe
 // pass 2 on a range shard (multi-GPU): window w of this shard receives one list per source rank,
 // laid out [source][w][cap] with counts [source][w] -- exactly what the all-to-all of the per-rank stagings
 // delivers.
-__global__ void __launch_bounds__(256) bloom_apply_sources(uint32_t *__restrict__ shard_words, const uint32_t *__restrict__ stage,
+static __global__ void __launch_bounds__(256) bloom_apply_sources(uint32_t *__restrict__ shard_words, const uint32_t *__restrict__ stage,
                                                            const unsigned int *__restrict__ cursors, uint32_t n_sources,
                                                            uint32_t wps, uint32_t cap, uint32_t window_log2,
                                                            uint32_t ctas_per_window) {

@@ -170,8 +170,8 @@ class ShardedBloomFilter:
         # run on torch's current stream so kernels, NCCL collectives and tensor ops are ordered without
         # host synchronization (handle 0 is the legacy default stream = cudaStreamLegacy, 0x1)
         self._ctx = context if context is not None else torch_stream_context(self.device)
-        if mode not in ("fused", "route", "gather"):
-            raise ValueError("mode must be 'fused', 'route' or 'gather'")
+        if mode not in ("p2p", "p2p_direct", "fused", "route", "gather"):
+            raise ValueError("mode must be 'p2p', 'p2p_direct', 'fused', 'route' or 'gather'")
         self.mode = mode
         self.chunk_keys = int(chunk_keys)
         h = C.c_void_p()
@@ -183,6 +183,7 @@ class ShardedBloomFilter:
         self._counts = None
         self._fused_bufs = None
         self._s_part = self._s_comm = self._ctx_part = None
+        self._p2p = None
 
     # -- properties in the reference's vocabulary
     @property
@@ -207,6 +208,9 @@ class ShardedBloomFilter:
         return self._els_added
 
     def close(self) -> None:
+        if getattr(self, "_p2p", None) is not None and _native._lib is not None:
+            _native._lib.pb_p2p_destroy(self._p2p["h"])
+            self._p2p = None
         if getattr(self, "_h", None) is not None and _native._lib is not None:
             _native._lib.pb_bloom_destroy(self._h)
             self._h = None
@@ -274,6 +278,10 @@ class ShardedBloomFilter:
             raise TypeError("fused/route modes take 16-byte keys; use mode='gather' for other widths")
         if self.mode == "fused":
             self._add_fused(t)
+            self._els_added += n
+            return
+        if self.mode in ("p2p", "p2p_direct"):
+            self._add_p2p(t)
             self._els_added += n
             return
         self._add_route(t, self.chunk_keys, worst_case=False)
@@ -388,6 +396,70 @@ class ShardedBloomFilter:
         if worst > b["ovf"].numel():
             # more strays than the list holds (e.g. one key repeated millions of times): OR is idempotent, so
             # simply run the whole batch again through the exact u64 route with worst-case slots
+            self._add_route(t, min(self.chunk_keys, 1 << 20), worst_case=True)
+        elif worst > 0:
+            self._route_indices(b["ovf"][: int(b["ovf_n"].item())])
+
+    # -- fused compute + exchange over NVLink peer memory: see pb_p2p_* in include/pb200.h
+    def _p2p_setup(self, chunk: int):
+        torch, dist = self._torch, self._dist
+        if self._p2p is not None and self._p2p["chunk"] >= chunk:
+            return self._p2p
+        if self._p2p is not None:
+            raise ValueError("the P2P mailbox was sized for smaller chunks; construct the filter with the final chunk_keys")
+        plan = self.plan
+        W = plan.total_windows
+        if self._s_part is None:
+            self._s_part = torch.cuda.Stream(device=self.device)
+            self._s_comm = torch.cuda.Stream(device=self.device)
+            self._ctx_part = _native.Context(self.device, stream=self._s_part.cuda_stream)
+        slack = C.c_uint64()
+        _native.call("pb_bloom_partition_slack", self._ctx.handle, chunk, self._k, W, C.byref(slack))
+        expect = chunk * self._k * (1 << plan.window_log2) / self._m
+        cap = int(expect * 1.03 + 6.0 * math.sqrt(expect + 1.0)) + slack.value
+        cap = (cap + 3) // 4 * 4
+        h = C.c_void_p()
+        _native.call("pb_p2p_create", self._ctx_part.handle, self.world, self.rank, plan.windows_per_rank, cap, C.byref(h))
+        _native.call("pb_p2p_set_direct", h, 1 if self.mode == "p2p_direct" else 0)
+        dev = f"cuda:{self.device}"
+        mine = np.zeros(64, dtype=np.uint8)
+        _native.call("pb_p2p_export", h, C.c_void_p(mine.ctypes.data))
+        allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, torch.from_numpy(mine).to(dev), group=self.group)
+        handles = np.ascontiguousarray(allh.cpu().numpy())
+        _native.call("pb_p2p_connect", h, C.c_void_p(handles.ctypes.data))
+        dist.barrier(group=self.group)  # every mailbox is mapped everywhere before anyone writes
+        self._p2p = {"chunk": chunk, "cap": cap, "h": h,
+                     "ovf": torch.empty(1 << 22, dtype=torch.int64, device=dev), "ovf_n": torch.zeros(1, dtype=torch.int64, device=dev)}
+        return self._p2p
+
+    def _add_p2p(self, t) -> None:
+        """pass 1 stores into the owners' mailboxes over NVLink (stream s_part); pass 2 on the filter's stream"""
+        torch, dist = self._torch, self._dist
+        plan = self.plan
+        n = int(t.shape[0])
+        n_chunks = torch.tensor([-(-n // self.chunk_keys)], dtype=torch.int64, device=t.device)
+        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)
+        n_chunks = int(n_chunks.item())
+        if n_chunks == 0:
+            return
+        b = self._p2p_setup(self.chunk_keys)
+        main = torch.cuda.current_stream(self.device)
+        b["ovf_n"].zero_()
+        self._s_part.wait_stream(main)
+        act = plan.active_windows(self.rank)
+        for ci in range(n_chunks):
+            lo = min(ci * self.chunk_keys, n)
+            hi = min(lo + self.chunk_keys, n)
+            kb = pack_keys(t[lo:hi]) if hi > lo else pack_keys(t[:0])
+            _native.call("pb_p2p_partition_send", b["h"], kb.ref(), self._m, self._k, plan.window_log2,
+                         C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
+            _native.call("pb_p2p_apply", b["h"], self._h, act, plan.window_log2)
+        main.wait_stream(self._s_part)  # (the last pass 2 on `main` already waited for every source's copies)
+        worst = b["ovf_n"].clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
+        worst = int(worst.item())
+        if worst > b["ovf"].numel():
             self._add_route(t, min(self.chunk_keys, 1 << 20), worst_case=True)
         elif worst > 0:
             self._route_indices(b["ovf"][: int(b["ovf_n"].item())])
