@@ -388,6 +388,13 @@ static uint32_t pick_quota(uint64_t n, uint32_t k, uint32_t n_windows, int grid)
     return q;
 }
 
+// 512-key tiles once a 256-key tile would give a window fewer than ~16 entries ("bloom_part_tile": 0 auto, 256, 512)
+static bool part_big_tile(const pb_ctx *ctx, uint32_t n_windows) {
+    if (ctx->bloom_part_tile == 512) return true;
+    if (ctx->bloom_part_tile == 256) return false;
+    return n_windows > 112;
+}
+
 struct PartPlan {
     bool use = false;
     uint32_t window_log2 = 0;
@@ -508,13 +515,14 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
         if (overlap && ctx->apply_pending[half]) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[half], 0));
         PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 4, ctx->stream));
         const int grid = std::min(pl.grid, grid_for(ctx, dk.n, 256, 4));
+        const bool big_tile = part_big_tile(ctx, pl.n_windows) && pl.version == 3 && grid >= 2;
         const uint4 *k4 = (const uint4 *)dk.data;
         launch_begin(ctx);
         switch (pl.ng * 100 + pl.kg) {
 #define PB_P2(KG, NG)                                                                                   \
     do {                                                                                                \
         if (pl.version == 2) bloom_part2_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd);    \
-        else bloom_part3_fixed16<KG, NG, false><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd, P2PDst{});                    \
+        else launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, dk.n, pd, P2PDst{});                           \
     } while (0)
             case 101: PB_P2(1, 1); break;
             case 102: PB_P2(2, 1); break;
@@ -866,11 +874,15 @@ int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits,
     pd.ovf_count = (unsigned long long *)ovf_count_dev;
     pd.ovf_cap = ovf_cap;
     const int grid = grid_for(ctx, keys->n, 256, 4);
+    const bool big_tile = part_big_tile(ctx, n_windows) && grid >= 2;
     const uint4 *k4 = (const uint4 *)keys->data;
     const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
     launch_begin(ctx);
     switch (ng * 100 + kg) {
-#define PB_P3(KG, NG) bloom_part3_fixed16<KG, NG, false><<<grid, 256, 0, ctx->stream>>>(k4, keys->n, pd, P2PDst{})
+#define PB_P3(KG, NG)                                                                                                   \
+    do {                                                                                                                \
+        launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, keys->n, pd, P2PDst{});                            \
+    } while (0)
         case 101: PB_P3(1, 1); break;
         case 102: PB_P3(2, 1); break;
         case 103: PB_P3(3, 1); break;

@@ -174,15 +174,17 @@ struct P2PDst {
     uint32_t src_rank;        // this GPU's block inside every destination's staging
 };
 
-template <int KG, int NG, bool P2P>
-__global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p, P2PDst dst) {
+// BS = threads (= keys) per tile: 256, or 512 when there are many windows (longer runs per window, the scan and
+// the barriers amortised over twice the entries)
+template <int KG, int NG, bool P2P, int BS = 256>
+__global__ void __launch_bounds__(BS, 1024 / BS) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p, P2PDst dst) {
     __shared__ uint32_t *wbase[P2P ? kMaxWindows2 : 1];  // P2P: start of window w's list in its owner's memory
     __shared__ uint32_t hist[2][kMaxWindows2];
     __shared__ uint32_t tbase[kMaxWindows2];       // window-relative list position of the tile's first entry
     __shared__ uint32_t wstart[kMaxWindows2 + 1];  // exclusive prefix sum of hist: start of the window's run in sorted[]
     __shared__ uint32_t cur[kMaxWindows2], lim[kMaxWindows2];
-    __shared__ uint32_t sorted_loc[256 * NG * KG];
-    __shared__ uint16_t sorted_win[256 * NG * KG];
+    __shared__ uint32_t sorted_loc[BS * NG * KG];
+    __shared__ uint16_t sorted_win[BS * NG * KG];
     const uint32_t tid = threadIdx.x;
     const uint32_t W = p.n_windows;
     const uint32_t mask = (1u << p.window_log2) - 1u;
@@ -300,6 +302,20 @@ __global__ void __launch_bounds__(256, 4) bloom_part3_fixed16(const uint4 *__res
         for (uint32_t q = cur[w]; q < e; ++q) list_of(w)[q] = kSentinel;
     }
     if (P2P) __threadfence_system();  // the entries must have reached the owners before the flags are raised
+}
+
+// host-side launcher: 512-key tiles only exist for k <= 8 (NG == 1): two index groups would not fit the 48 KB of
+// static shared memory
+template <int KG, int NG, bool P2P>
+static void launch_part3(bool big_tile, int grid, cudaStream_t stream, const uint4 *keys, uint64_t n, const Part2Dev &pd,
+                         const P2PDst &dst) {
+    if constexpr (NG == 1) {
+        if (big_tile && grid >= 2) {
+            bloom_part3_fixed16<KG, NG, P2P, 512><<<grid / 2, 512, 0, stream>>>(keys, n, pd, dst);
+            return;
+        }
+    }
+    bloom_part3_fixed16<KG, NG, P2P, 256><<<grid, 256, 0, stream>>>(keys, n, pd, dst);
 }
 
 // pass 2: one window at a time (launch order); its bitmap slice stays L2 resident while its list streams by

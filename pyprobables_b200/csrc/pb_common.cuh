@@ -71,6 +71,7 @@ struct pb_ctx {
     int64_t bloom_window_log2_bits = 27; // 2^27 bits = 16 MiB of bitmap per L2 window (r1 sweeps: best with overlap)
     int64_t bloom_apply_cpw_per_sm = 4;  // apply pass: CTAs per window = this x SMs (at most ~2 windows in flight, so the
                                          // windows being updated stay L2 resident; 4 x 32 MiB at once thrashed: r1 sweep)
+    int64_t bloom_part_tile = 0;         // keys per pass-1 tile: 0 auto (512 beyond 112 windows), 256, 512
     int64_t bloom_overlap = 1;           // run pass 2 of chunk i on aux_stream while pass 1 of chunk i+1 runs
     int64_t bloom_part_version = 3;      // 1: first partition kernels, 2: quota cursors + prefetch, 3: + smem-sorted coalesced copy-out
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert

@@ -431,6 +431,7 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "bloom_apply_cpw_per_sm")) return &ctx->bloom_apply_cpw_per_sm;
     if (!strcmp(name, "bloom_part_version")) return &ctx->bloom_part_version;
     if (!strcmp(name, "bloom_overlap")) return &ctx->bloom_overlap;
+    if (!strcmp(name, "bloom_part_tile")) return &ctx->bloom_part_tile;
     if (!strcmp(name, "h2d_chunk_keys")) return &ctx->h2d_chunk_keys;
     if (!strcmp(name, "cms_aggregate")) return &ctx->cms_aggregate;
     if (!strcmp(name, "cuckoo_serial")) return &ctx->cuckoo_serial;

@@ -253,6 +253,7 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
         pd.k = k;
         pd.recip_fits32 = num_bits > (1ull << 32) ? 1u : 0u;
         const int grid = grid_for(ctx, keys->n, 256, 4);
+        const bool big_tile = grid >= 2 && (ctx->bloom_part_tile == 512 || (ctx->bloom_part_tile != 256 && W > 112));
         {
             const double per = (double)keys->n * k / ((double)W * (double)std::max(grid, 1));
             uint32_t q = 32;
@@ -273,8 +274,8 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
         switch (ng * 100 + kg) {
 #define PB_P3(KG, NG)                                                                                          \
     do {                                                                                                       \
-        if (p->direct) bloom_part3_fixed16<KG, NG, true><<<grid, 256, 0, ctx->stream>>>(k4, keys->n, pd, dst);  \
-        else bloom_part3_fixed16<KG, NG, false><<<grid, 256, 0, ctx->stream>>>(k4, keys->n, pd, dst);           \
+        if (p->direct) launch_part3<KG, NG, true>(big_tile, grid, ctx->stream, k4, keys->n, pd, dst);   \
+        else launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, keys->n, pd, dst);            \
     } while (0)
             case 101: PB_P3(1, 1); break;
             case 102: PB_P3(2, 1); break;
