@@ -123,6 +123,10 @@ int pb_bloom_add_hashes(pb_bloom *b, const uint64_t *hashes, uint64_t n, int on_
 int pb_bloom_check_hashes(pb_bloom *b, const uint64_t *hashes, uint64_t n, int on_device, uint8_t *out,
                           int out_on_device);
 int pb_bloom_popcount(pb_bloom *b, uint64_t *out); /* bloom.py:552-557 */
+/* BloomFilter.union (op 0) / intersection (op 1), bloom.py:371-428: dst = a op b for same-shaped filters on one device */
+int pb_bloom_combine(pb_bloom *dst, pb_bloom *a, pb_bloom *b, int op);
+/* jaccard_index (bloom.py:430-460): counts[0] = popcount(a | b), counts[1] = popcount(a & b) */
+int pb_bloom_pair_popcounts(pb_bloom *a, pb_bloom *b, uint64_t *counts);
 /* multi-GPU range sharding: this handle owns bits [lo, hi) of a num_bits-bit filter.
  * Keys are hashed against the GLOBAL num_bits; only indices inside [lo, hi) touch this shard. */
 int pb_bloom_create_shard(pb_ctx *ctx, uint64_t num_bits, uint32_t k, uint64_t lo_bit, uint64_t hi_bit,

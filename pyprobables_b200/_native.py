@@ -104,6 +104,8 @@ SIGNATURES: dict[str, list] = {
     "pb_bloom_add_hashes": [_vp, _vp, _u64, _i32],
     "pb_bloom_check_hashes": [_vp, _vp, _u64, _i32, _vp, _i32],
     "pb_bloom_popcount": [_vp, _P(_u64)],
+    "pb_bloom_combine": [_vp, _vp, _vp, _i32],
+    "pb_bloom_pair_popcounts": [_vp, _vp, _P(_u64)],
     "pb_bloom_create_shard": [_vp, _u64, _u32, _u64, _u64, _P(_vp)],
     "pb_bloom_route_keys": [_vp, _KP, _u64, _u32, _u64, _u32, _vp, _u64, _vp],
     "pb_bloom_partition_keys": [_vp, _KP, _u64, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u64, _vp],

@@ -22,7 +22,7 @@ from pathlib import Path
 import numpy as np
 
 from . import _native
-from .exceptions import InitializationError
+from .exceptions import InitializationError, SimilarityError
 from .hashes import default_fnv_1a, is_default_hash
 from .keys import pack_keys
 
@@ -295,6 +295,46 @@ class BloomFilter:
             f"\tnumber bits set: {self._cnt_number_bits_set()}\n"
             f"\tis on disk: {'yes' if self.is_on_disk else 'no'}\n"
         )
+
+    # ------------------------------------------------------------------ set algebra (bloom.py:371-460, :563-568)
+    def _verify_bloom_similarity(self, second) -> bool:
+        return not (
+            self.number_hashes != second.number_hashes
+            or self.number_bits != second.number_bits
+            or self.hashes("test") != second.hashes("test")
+        )
+
+    def _check_second(self, second) -> None:
+        if not isinstance(second, BloomFilter):
+            raise TypeError("The parameter second must be of type BloomFilter or a BloomFilterOnDisk")
+        if self._verify_bloom_similarity(second) is False:
+            raise SimilarityError("Bloom Filters are not similar")
+
+    def _combined(self, second, op: int) -> "BloomFilter":
+        self._check_second(second)
+        res = BloomFilter(self.estimated_elements, self.false_positive_rate, hash_function=self._hash_func
+                          if not self._fused else None, context=self._ctx)
+        res._hash_func, res._fused = self._hash_func, self._fused
+        _native.call("pb_bloom_combine", res._h, self._h, second._h, op)
+        res.elements_added = res.estimate_elements()
+        return res
+
+    def intersection(self, second) -> "BloomFilter":
+        """bloom.py:371-399 (bitwise AND on the device)"""
+        return self._combined(second, 1)
+
+    def union(self, second) -> "BloomFilter":
+        """bloom.py:401-428 (bitwise OR on the device)"""
+        return self._combined(second, 0)
+
+    def jaccard_index(self, second) -> float:
+        """bloom.py:430-460"""
+        self._check_second(second)
+        counts = (C.c_uint64 * 2)()
+        _native.call("pb_bloom_pair_popcounts", self._h, second._h, counts)
+        if counts[0] == 0:
+            return 1.0
+        return counts[1] / counts[0]
 
     # ------------------------------------------------------------------ wire formats (bloom.py:274-338, :504-550)
     def export_hex(self) -> str:

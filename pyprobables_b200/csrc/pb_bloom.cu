@@ -179,6 +179,37 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// bloom.py:371-428: res = a | b (op 0) or a & b (op 1), streaming 128-bit words
+__global__ void __launch_bounds__(256) bloom_combine_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ a,
+                                                            const uint4 *__restrict__ b, uint64_t n4, int op) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = __ldcs(a + i), y = __ldcs(b + i);
+        uint4 r;
+        if (op == 0) r = make_uint4(x.x | y.x, x.y | y.y, x.z | y.z, x.w | y.w);
+        else r = make_uint4(x.x & y.x, x.y & y.y, x.z & y.z, x.w & y.w);
+        __stcs(dst + i, r);
+    }
+}
+
+// bloom.py:430-460: popcounts of a | b and a & b in one pass
+__global__ void __launch_bounds__(256) bloom_pair_popcount_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
+                                                                  uint64_t n4, unsigned long long *out) {
+    unsigned long long cu = 0, ci = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = __ldcs(a + i), y = __ldcs(b + i);
+        cu += __popc(x.x | y.x) + __popc(x.y | y.y) + __popc(x.z | y.z) + __popc(x.w | y.w);
+        ci += __popc(x.x & y.x) + __popc(x.y & y.y) + __popc(x.z & y.z) + __popc(x.w & y.w);
+    }
+    for (int o = 16; o; o >>= 1) {
+        cu += __shfl_xor_sync(0xffffffffu, cu, o);
+        ci += __shfl_xor_sync(0xffffffffu, ci, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cu) atomicAdd(out, cu);
+        if (ci) atomicAdd(out + 1, ci);
+    }
+}
+
 // bloom.py:552-557
 __global__ void __launch_bounds__(256) popcount_kernel(const uint4 *__restrict__ w, uint64_t n4, unsigned long long *out) {
     unsigned long long c = 0;
@@ -807,6 +838,47 @@ int pb_bloom_popcount(pb_bloom *b, uint64_t *out) {
     PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = *(uint64_t *)ctx->pinned_small;
+    return PB_OK;
+}
+
+static int same_shape(const pb_bloom *a, const pb_bloom *b) {
+    return a->num_bits == b->num_bits && a->lo_bit == b->lo_bit && a->hi_bit == b->hi_bit && a->ctx->device == b->ctx->device;
+}
+
+// BloomFilter.union / intersection (bloom.py:371-428): dst = a | b (op 0) or a & b (op 1); dst may be a or b
+int pb_bloom_combine(pb_bloom *dst, pb_bloom *a, pb_bloom *b, int op) {
+    PB_REQUIRE(dst && a && b, "NULL argument");
+    PB_REQUIRE(op == 0 || op == 1, "op must be 0 (union) or 1 (intersection)");
+    PB_REQUIRE(same_shape(dst, a) && same_shape(dst, b), "Bloom Filters are not similar");
+    pb_ctx *ctx = dst->ctx;
+    DeviceGuard g(ctx->device);
+    if (a->ctx != ctx) PB_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    if (b->ctx != ctx) PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    launch_begin(ctx);
+    bloom_combine_kernel<<<grid_for(ctx, dst->nwords / 4, 256, 8), 256, 0, ctx->stream>>>((uint4 *)dst->words, (const uint4 *)a->words,
+                                                                                          (const uint4 *)b->words, dst->nwords / 4, op);
+    return check_launch(ctx, "bloom_combine");
+}
+
+// counts[0] = bits set in a | b, counts[1] = bits set in a & b (jaccard_index, bloom.py:430-460)
+int pb_bloom_pair_popcounts(pb_bloom *a, pb_bloom *b, uint64_t *counts) {
+    PB_REQUIRE(a && b && counts, "NULL argument");
+    PB_REQUIRE(same_shape(a, b), "Bloom Filters are not similar");
+    pb_ctx *ctx = a->ctx;
+    DeviceGuard g(ctx->device);
+    if (b->ctx != ctx) PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = (unsigned long long *)ctx->small.p + 40;
+    PB_CUDA(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+    launch_begin(ctx);
+    bloom_pair_popcount_kernel<<<grid_for(ctx, a->nwords / 4, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)a->words,
+                                                                                              (const uint4 *)b->words, a->nwords / 4, acc);
+    PB_TRY(check_launch(ctx, "bloom_pair_popcount"));
+    uint64_t *h = (uint64_t *)((uint8_t *)ctx->pinned_small + 512);
+    PB_CUDA(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    counts[0] = h[0];
+    counts[1] = h[1];
     return PB_OK;
 }
 
