@@ -176,8 +176,10 @@ struct P2PDst {
 
 // BS = threads (= keys) per tile: 256, or 512 when there are many windows (longer runs per window, the scan and
 // the barriers amortised over twice the entries)
+// 56 registers at most: four 256-thread CTAs then leave 8192 registers per SM, exactly one pass-2 CTA, which is what
+// lets pass 2 of the previous chunk run beside this kernel (at 64 registers the overlap disappears)
 template <int KG, int NG, bool P2P, int BS = 256>
-__global__ void __launch_bounds__(BS, 1024 / BS) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p, P2PDst dst) {
+__global__ void __maxnreg__(56) bloom_part3_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p, P2PDst dst) {
     __shared__ uint32_t *wbase[P2P ? kMaxWindows2 : 1];  // P2P: start of window w's list in its owner's memory
     __shared__ uint32_t hist[2][kMaxWindows2];
     __shared__ uint32_t tbase[kMaxWindows2];       // window-relative list position of the tile's first entry

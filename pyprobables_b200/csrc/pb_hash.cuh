@@ -20,6 +20,23 @@ constexpr uint64_t kFnvPrime = 0x100000001B3ULL;       // hashes.py:97  (= 2^40 
 PB_HD uint64_t fnv_init(uint64_t seed) { return kFnvBasis + 31ULL * seed; }  // hashes.py:96
 PB_HD uint64_t fnv_step(uint64_t h, uint32_t sym) { return (h ^ (uint64_t)sym) * kFnvPrime; }  // :100-102
 
+#if defined(__CUDA_ARCH__)
+// One FNV-1a step on a hash held as two 32-bit halves, pinned to four SASS instructions.  The 64-bit product
+// h * (2^40 + 0x1B3) is  lo' = low32(x*0x1B3),  hi' = (hi*0x1B3 + high32(x*0x1B3)) + (x << 8)  with x = lo ^ sym.
+// Left to itself nvcc reassociates the sum and emits five instructions per step (IMAD, IMAD x*0x100+.., IMAD.WIDE,
+// IMAD.IADD, LOP3: 1032 instructions per 16-byte key at k = 7 in the round-1 profile, and the kernel is
+// issue bound).  The explicit mad chain below makes ptxas emit exactly LOP3, IMAD.WIDE.U32, IMAD, LEA.
+__device__ __forceinline__ void fnv_step_halves(uint32_t &lo, uint32_t &hi, uint32_t sym) {
+    const uint32_t x = lo ^ sym;
+    uint32_t plo, phi, t, h2;
+    asm("{ .reg .b64 p; mul.wide.u32 p, %2, 0x1b3; mov.b64 {%0, %1}, p; }" : "=r"(plo), "=r"(phi) : "r"(x));
+    asm("mad.lo.u32 %0, %1, 0x1b3, %2;" : "=r"(t) : "r"(hi), "r"(phi));
+    asm("mad.lo.u32 %0, %1, 0x100, %2;" : "=r"(h2) : "r"(x), "r"(t));
+    lo = plo;
+    hi = h2;
+}
+#endif
+
 PB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
     return __umul64hi(a, b);

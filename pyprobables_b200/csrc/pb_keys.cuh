@@ -35,18 +35,25 @@ inline int pick_group(uint32_t k) {
 // ---- fixed 16-byte keys held in registers ---------------------------------------------------------
 template <int KG>
 __device__ __forceinline__ void fnv_group_16(const uint4 &w, uint32_t seed0, uint64_t (&h)[KG]) {
+    uint32_t lo[KG], hi[KG];
 #pragma unroll
-    for (int j = 0; j < KG; ++j) h[j] = fnv_init(seed0 + j);
+    for (int j = 0; j < KG; ++j) {
+        const uint64_t h0 = fnv_init(seed0 + j);
+        lo[j] = (uint32_t)h0;
+        hi[j] = (uint32_t)(h0 >> 32);
+    }
     const uint32_t words[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const uint32_t sym = (words[wi] >> (8 * b)) & 0xFFu;
+            const uint32_t sym = __byte_perm(words[wi], 0u, 0x4440 + b);  // byte b, zero extended (one PRMT)
 #pragma unroll
-            for (int j = 0; j < KG; ++j) h[j] = fnv_step(h[j], sym);
+            for (int j = 0; j < KG; ++j) fnv_step_halves(lo[j], hi[j], sym);
         }
     }
+#pragma unroll
+    for (int j = 0; j < KG; ++j) h[j] = ((uint64_t)hi[j] << 32) | lo[j];
 }
 
 // ---- generic keys: symbols behind a pointer (shared or global) -------------------------------------
