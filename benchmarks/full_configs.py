@@ -22,6 +22,9 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
+OPTS: list = []
+
+
 def md5(a) -> str:
     return hashlib.md5(memoryview(np.ascontiguousarray(a))).hexdigest()
 
@@ -33,6 +36,10 @@ def setup():
 
     stream = torch.cuda.Stream()
     ctx = pb.Context(0, stream=stream.cuda_stream)
+    for kv in OPTS:
+        name, value = kv.split("=")
+        ctx.set_option(name, int(value))
+    ctx.set_option("kernel_timing", 1)
     return torch, pb, stream, ctx
 
 
@@ -155,6 +162,7 @@ def run_cms(a):
     out["estimates_equal_oracle"] = bool((est.cpu().numpy() == want).all())
     out["estimate_rank1"] = int(want[0])
     out["max_bin"] = int(bins.max())
+    out["kernels_ms"] = {k: {"launches": v[0], "total_ms": round(v[1], 3)} for k, v in ctx.kernel_times().items()}
     out["parity"] = bool(out["bins_md5"] == out["oracle_bins_md5"] and out["estimates_equal_oracle"]
                          and out["elements_added"] == oc.elements_added == n)
     print(json.dumps(out), flush=True)
@@ -257,6 +265,7 @@ def run_cuckoo(a):
         out["absent_probe_positives"] = positives
         out["absent_probe_fpr"] = positives / pm
         out["absent_probes_equal_oracle"] = fps_probe_all_equal
+    out["kernels_ms"] = {k: {"launches": v[0], "total_ms": round(v[1], 3)} for k, v in ctx.kernel_times().items()}
     out["parity"] = bool(failed_total == 0 and all_present and same_set and fps_probe_all_equal
                          and out["stored_count"] == added == out["distinct_fingerprints_oracle"])
     print(json.dumps(out), flush=True)
@@ -269,7 +278,9 @@ def main():
     ap.add_argument("--keys", type=int, default=10**9)
     ap.add_argument("--absent", type=int, default=10**8)
     ap.add_argument("--capacity-log2", type=int, default=28)
+    ap.add_argument("--opt", action="append", default=[], help="context option name=value (repeatable)")
     a = ap.parse_args()
+    OPTS.extend(a.opt)
     ok = {"bloom": run_bloom, "cms": run_cms, "cuckoo": run_cuckoo}[a.which](a)
     sys.exit(0 if ok else 1)
 

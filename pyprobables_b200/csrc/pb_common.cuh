@@ -77,6 +77,7 @@ struct pb_ctx {
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics
+    int64_t cms_hot_cache = 1;           // per-CTA shared-memory write-back cache for hot counters (safe path)
     int64_t cuckoo_serial = 0;           // 1: one-thread in-order cuckoo insert (reference append order)
     int64_t kernel_timing = 0;           // 1: bracket the hot kernels with CUDA events (bench roofline)
     std::vector<pb_timed_launch> timed;

@@ -434,6 +434,7 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "bloom_part_tile")) return &ctx->bloom_part_tile;
     if (!strcmp(name, "h2d_chunk_keys")) return &ctx->h2d_chunk_keys;
     if (!strcmp(name, "cms_aggregate")) return &ctx->cms_aggregate;
+    if (!strcmp(name, "cms_hot_cache")) return &ctx->cms_hot_cache;
     if (!strcmp(name, "cuckoo_serial")) return &ctx->cuckoo_serial;
     if (!strcmp(name, "kernel_timing")) return &ctx->kernel_timing;
     return nullptr;

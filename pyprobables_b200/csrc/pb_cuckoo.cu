@@ -99,6 +99,16 @@ __device__ __forceinline__ bool bucket_place(const CuckooDev &c, uint64_t b, uin
     return false;
 }
 
+// bucket_place for 4-slot buckets from an already loaded snapshot of the bucket
+__device__ __forceinline__ bool bucket_place_from(const CuckooDev &c, uint64_t b, uint32_t fp, const uint4 &v) {
+    uint32_t *s = c.slots + b * 4;
+    if (v.x == 0 && atomicCAS(s + 0, 0u, fp) == 0u) return true;
+    if (v.y == 0 && atomicCAS(s + 1, 0u, fp) == 0u) return true;
+    if (v.z == 0 && atomicCAS(s + 2, 0u, fp) == 0u) return true;
+    if (v.w == 0 && atomicCAS(s + 3, 0u, fp) == 0u) return true;
+    return false;
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x) { return sm64(x); }
 
 // cuckoo.py:361-392 for one fingerprint that is known to be absent.  Returns true when everything found
@@ -107,8 +117,17 @@ template <int BS>
 __device__ __forceinline__ bool cuckoo_insert_one(const CuckooDev &c, uint32_t &fp, uint64_t rng) {
     uint64_t i1, i2;
     cuckoo_buckets(c, fp, i1, i2);
-    if (bucket_place<BS>(c, i1, fp)) return true;  // :363-365
-    if (bucket_place<BS>(c, i2, fp)) return true;  // :366-368
+    if (BS == 4) {
+        // both candidate buckets are fetched before either is examined: one DRAM round trip instead of two when
+        // idx_1 is full (the insert kernel is bound by exactly this latency chain at high load)
+        const uint4 v1 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i1);
+        const uint4 v2 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i2);
+        if (bucket_place_from(c, i1, fp, v1)) return true;  // :363-365
+        if (bucket_place_from(c, i2, fp, v2)) return true;  // :366-368
+    } else {
+        if (bucket_place<BS>(c, i1, fp)) return true;  // :363-365
+        if (bucket_place<BS>(c, i2, fp)) return true;  // :366-368
+    }
     rng = mix64(rng ^ fp);
     uint64_t idx = (rng & 1ull) ? i2 : i1;  // :373
     for (uint32_t s = 0; s < c.max_swaps; ++s) {
@@ -140,7 +159,9 @@ __device__ __forceinline__ void claim_filter(const CuckooDev &c, uint32_t fp, bo
             if ((old & bit) == 0u) {  // this thread owns fp for the batch
                 uint64_t i1, i2;
                 cuckoo_buckets(c, fp, i1, i2);
-                is_new = !(bucket_has<BS>(c, i1, fp) || bucket_has<BS>(c, i2, fp));  // :300-302
+                const bool in1 = bucket_has<BS>(c, i1, fp);  // both probes in flight together (no short circuit)
+                const bool in2 = bucket_has<BS>(c, i2, fp);
+                is_new = !(in1 | in2);  // :300-302
             }
         }
     }

@@ -44,12 +44,10 @@ def default_fnv_1a(key: KeyT, depth: int = 1) -> list:
 def fnv_1a(key: KeyT, seed: int = 0) -> int:
     """64-bit FNV-1a started from basis + 31*seed (hashes.py:86-103)"""
     seed = int(seed)
-    if 0 <= seed < 64:
-        return int(hash_many([key], seed + 1)[0, seed])
-    # large seeds: h0 = basis + 31*seed only shifts the start value; seeds are additive mod 2^64, and the
-    # device evaluates seeds 0..depth-1, so fold the request into an equivalent small problem on the host
-    # side of the plugin API by hashing with the generic pre-seeded entry.
-    raise ValueError("fnv_1a: seed must be in 0..63 (default_fnv_1a uses seeds 0..depth-1)")
+    if not 0 <= seed < 64:
+        # the device entry point evaluates seeds 0..depth-1 (what default_fnv_1a and the filters use)
+        raise ValueError("fnv_1a: seed must be in 0..63")
+    return int(hash_many([key], seed + 1)[0, seed])
 
 
 def hash_with_depth_bytes(func):
