@@ -244,6 +244,9 @@ def run_ours(args) -> None:
     ctx.set_option("bloom_insert_mode", args.insert_mode)
     if args.window_log2:
         ctx.set_option("bloom_window_log2_bits", args.window_log2)
+    for kv in args.opt:
+        name, value = kv.split("=")
+        ctx.set_option(name, int(value))
 
     with torch.cuda.stream(stream):
         keys = torch.empty((n_keys, 16), dtype=torch.uint8, device=dev)
@@ -279,6 +282,10 @@ def run_ours(args) -> None:
             step()
         barrier()
         ctxs = [ctx] + ([filt._ctx_part] if getattr(filt, "_ctx_part", None) is not None else [])
+        for c in ctxs[1:]:
+            for kv in args.opt:
+                name, value = kv.split("=")
+                c.set_option(name, int(value))
         for c in ctxs:
             c.set_option("kernel_timing", 1)
             c.kernel_times()
@@ -438,6 +445,7 @@ def main() -> None:
     ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "p2p_direct", "fused", "route", "gather"])
     ap.add_argument("--insert-mode", type=int, default=0, help="bloom_insert_mode: 0 auto, 1 direct RED, 2 partitioned")
     ap.add_argument("--window-log2", type=int, default=0, help="bloom_window_log2_bits override")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable), e.g. bloom_part_tile=256")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

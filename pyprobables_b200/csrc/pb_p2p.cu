@@ -1,10 +1,12 @@
 // pb_p2p.cu -- the multi-GPU Bloom insert as ONE fused compute + exchange kernel over NVLink peer memory.
 //
 // Every rank owns a "mailbox" in its own HBM (cudaMalloc'd, exported with CUDA IPC and mapped by every peer):
-//     recv_stage[2][n_src][wps][cap]   window lists, one block per source rank, double buffered by chunk parity
-//     recv_cur  [2][n_src][wps]        entries per list
-//     data_flag [2][n_src]             written by source s: "chunk seq of mine is complete in your half h"
-//     done_flag [2][n_dst]             written by destination d into the SOURCE's mailbox: "I applied your chunk seq"
+//     recv_stage[3][n_src][wps][cap]   window lists, one block per source rank; three buffers rotate by chunk number
+//     recv_cur  [3][n_src][wps]        entries per list
+//     data_flag [3][n_src]             written by source s: "chunk seq of mine is complete in your buffer h"
+//     done_flag [3][n_dst]             written by destination d into the SOURCE's mailbox: "I applied your chunk seq"
+// Three buffers, not two: with two, pass 1 of chunk c+2 would have to wait for pass 2 of chunk c on every
+// destination (pass 1 + copy + pass 2 > 2 x pass 1), a bubble in every second chunk and no slack for rank skew.
 // Pass 1 (bloom_part3_fixed16<.., P2P = true>) hashes a chunk of local keys, bins the bit indices by global
 // window and stores every entry straight into the list of its window inside the OWNER's mailbox -- the
 // all-to-all is the kernel's own coalesced stores travelling over NVLink while the next tile is being hashed.
@@ -27,6 +29,8 @@ uint32_t *bloom_words(pb_bloom *b);
 pb_ctx *bloom_ctx(pb_bloom *b);
 }  // namespace pb
 
+constexpr int kBufs = 3;
+
 struct pb_p2p {
     pb_ctx *send_ctx = nullptr;
     uint32_t world = 0, rank = 0, wps = 0, cap = 0;
@@ -34,23 +38,25 @@ struct pb_p2p {
     uint8_t *peer[16] = {nullptr};  // mapped mailboxes (peer[rank] == local)
     bool opened[16] = {false};
     size_t stage_bytes = 0, cur_bytes = 0, total_bytes = 0;
-    unsigned int *scur[2] = {nullptr, nullptr};  // local cursors of the chunk being partitioned [world*wps], per half
+    unsigned int *scur[kBufs] = {nullptr, nullptr, nullptr};  // local cursors of the chunk being partitioned [world*wps], per half
     uint64_t send_seq = 0, apply_seq = 0;
     // exchange variant: 1 = pass 1 stores straight into the owners' mailboxes (SM stores over NVLink);
     // 0 = pass 1 fills a local staging and the copy engines push every destination's block (DMA over NVLink),
     // which leaves the SMs to the two compute passes
     int direct = 0;
-    uint32_t *lstage[2] = {nullptr, nullptr};  // local staging halves (DMA variant), allocated on first use
+    uint32_t *lstage[kBufs] = {nullptr, nullptr, nullptr};  // local staging halves (DMA variant), allocated on first use
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_part[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_part[kBufs] = {nullptr, nullptr, nullptr}, ev_copy[kBufs] = {nullptr, nullptr, nullptr};
 };
 
 namespace pb {
 
 static size_t off_stage(const pb_p2p *p, int h) { return (size_t)h * p->stage_bytes; }
-static size_t off_cur(const pb_p2p *p, int h) { return 2 * p->stage_bytes + (size_t)h * p->cur_bytes; }
-static size_t off_data_flag(const pb_p2p *p, int h) { return 2 * p->stage_bytes + 2 * p->cur_bytes + (size_t)h * 16 * 8; }
-static size_t off_done_flag(const pb_p2p *p, int h) { return 2 * p->stage_bytes + 2 * p->cur_bytes + 2 * 16 * 8 + (size_t)h * 16 * 8; }
+static size_t off_cur(const pb_p2p *p, int h) { return kBufs * p->stage_bytes + (size_t)h * p->cur_bytes; }
+static size_t off_data_flag(const pb_p2p *p, int h) { return kBufs * p->stage_bytes + kBufs * p->cur_bytes + (size_t)h * 16 * 8; }
+static size_t off_done_flag(const pb_p2p *p, int h) {
+    return kBufs * p->stage_bytes + kBufs * p->cur_bytes + (size_t)kBufs * 16 * 8 + (size_t)h * 16 * 8;
+}
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
@@ -119,7 +125,7 @@ int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t wind
     p->cap = cap;
     p->stage_bytes = ((size_t)world * windows_per_rank * cap * 4 + 255) & ~(size_t)255;
     p->cur_bytes = ((size_t)world * windows_per_rank * 4 + 255) & ~(size_t)255;
-    p->total_bytes = 2 * p->stage_bytes + 2 * p->cur_bytes + 4 * 16 * 8;
+    p->total_bytes = kBufs * p->stage_bytes + kBufs * p->cur_bytes + 2 * (size_t)kBufs * 16 * 8;
     cudaError_t e = cudaMalloc(&p->local, p->total_bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -127,7 +133,7 @@ int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t wind
         delete p;
         return PB_ERR_OOM;
     }
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kBufs; ++h) {
         e = cudaMalloc(&p->scur[h], (size_t)world * windows_per_rank * 4);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -141,7 +147,7 @@ int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t wind
     }
     PB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     // flags and counts start at zero; the lists need no initialisation
-    PB_CUDA(cudaMemset(p->local + 2 * p->stage_bytes, 0, 2 * p->cur_bytes + 4 * 16 * 8));
+    PB_CUDA(cudaMemset(p->local + kBufs * p->stage_bytes, 0, kBufs * p->cur_bytes + 2 * (size_t)kBufs * 16 * 8));
     p->peer[rank] = p->local;
     *out = p;
     return PB_OK;
@@ -183,7 +189,7 @@ int pb_p2p_destroy(pb_p2p *p) {
     cudaDeviceSynchronize();
     for (uint32_t r = 0; r < p->world; ++r)
         if (p->opened[r]) cudaIpcCloseMemHandle(p->peer[r]);
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kBufs; ++h) {
         cudaFree(p->scur[h]);
         if (p->lstage[h]) cudaFree(p->lstage[h]);
         if (p->ev_part[h]) cudaEventDestroy(p->ev_part[h]);
@@ -218,10 +224,10 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
     pb_ctx *ctx = p->send_ctx;
     DeviceGuard g(ctx->device);
     const unsigned long long seq = ++p->send_seq;
-    const int h = (int)(seq & 1);
+    const int h = (int)(seq % kBufs);
     const size_t block_bytes = (size_t)p->wps * p->cap * 4;  // one destination's windows
     if (!p->direct) {
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < kBufs; ++q) {
             if (!p->lstage[q]) {
                 cudaError_t e = cudaMalloc(&p->lstage[q], block_bytes * p->world);
                 if (e != cudaSuccess) {
@@ -231,12 +237,12 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
                 }
             }
         }
-        // the copies that read this local half two chunks ago are done
-        if (seq > 2) PB_CUDA(cudaStreamWaitEvent(ctx->stream, p->ev_copy[h], 0));
-    } else if (seq > 2) {
-        // direct stores: every destination must have applied the chunk that used this mailbox half last
+        // the copies that read this local buffer kBufs chunks ago are done
+        if (seq > kBufs) PB_CUDA(cudaStreamWaitEvent(ctx->stream, p->ev_copy[h], 0));
+    } else if (seq > kBufs) {
+        // direct stores: every destination must have applied the chunk that used this mailbox buffer last
         p2p_wait_flags<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(p->local + off_done_flag(p, h)), p->world,
-                                                 seq - 2);
+                                                 seq - kBufs);
         PB_TRY(check_launch(ctx, "p2p_wait"));
     }
     PB_CUDA(cudaMemsetAsync(p->scur[h], 0, (size_t)W * 4, ctx->stream));
@@ -304,8 +310,9 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
     cudaStream_t cs = p->copy_stream;
     PB_CUDA(cudaEventRecord(p->ev_part[h], ctx->stream));
     PB_CUDA(cudaStreamWaitEvent(cs, p->ev_part[h], 0));
-    if (seq > 2) {
-        p2p_wait_flags<<<1, 32, 0, cs>>>(reinterpret_cast<const unsigned long long *>(p->local + off_done_flag(p, h)), p->world, seq - 2);
+    if (seq > kBufs) {
+        p2p_wait_flags<<<1, 32, 0, cs>>>(reinterpret_cast<const unsigned long long *>(p->local + off_done_flag(p, h)), p->world,
+                                         seq - kBufs);
         PB_TRY(check_launch(ctx, "p2p_wait", cs));
     }
     for (uint32_t i = 0; i < p->world; ++i) {
@@ -328,7 +335,7 @@ int pb_p2p_apply(pb_p2p *p, pb_bloom *shard, uint32_t active_windows, uint32_t w
     pb_ctx *ctx = shard ? bloom_ctx(shard) : p->send_ctx;
     DeviceGuard g(ctx->device);
     const unsigned long long seq = ++p->apply_seq;
-    const int h = (int)(seq & 1);
+    const int h = (int)(seq % kBufs);
     p2p_wait_flags<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(p->local + off_data_flag(p, h)), p->world, seq);
     PB_TRY(check_launch(ctx, "p2p_wait"));
     if (active_windows) {
