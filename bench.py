@@ -278,6 +278,9 @@ def run_ours(args) -> None:
                 dist.barrier()
             torch.cuda.synchronize()
 
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()  # before the warm-up: nvidia-smi needs up to a second before its first sample
         for _ in range(max(args.warmup, 0)):
             step()
         barrier()
@@ -290,9 +293,6 @@ def run_ours(args) -> None:
             c.set_option("kernel_timing", 1)
             c.kernel_times()
         launches0 = sum(c.launch_count for c in ctxs)
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
