@@ -78,7 +78,8 @@ class BloomFilter:
         device: int = 0,
         context=None,
     ):
-        self._ctx = context if context is not None else _native.default_context(device)
+        self._ctx_arg = (context, device)  # resolved in _set_values(): argument errors surface before any device work
+        self._ctx = context
         self._h = None
         self._on_disk = False
         self._els_added = 0
@@ -102,6 +103,8 @@ class BloomFilter:
         self._hash_func = hash_func if hash_func is not None else default_fnv_1a
         self._fused = is_default_hash(hash_func)
         self._els_added = 0
+        if self._ctx is None:
+            self._ctx = _native.default_context(self._ctx_arg[1])
         if self._h is not None:
             _native.lib().pb_bloom_destroy(self._h)
         h = C.c_void_p()

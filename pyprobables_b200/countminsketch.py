@@ -23,7 +23,7 @@ from pathlib import Path
 import numpy as np
 
 from . import _native
-from .constants import INT32_T_MAX, INT32_T_MIN, INT64_T_MAX, INT64_T_MIN
+from ._limits import INT64_T_MAX, INT64_T_MIN
 from .exceptions import CountMinSketchError, InitializationError, NotSupportedError
 from .hashes import default_fnv_1a, is_default_hash
 from .keys import pack_keys
@@ -49,7 +49,8 @@ class CountMinSketch:
         device: int = 0,
         context=None,
     ):
-        self._ctx = context if context is not None else _native.default_context(device)
+        self._ctx_arg = (context, device)  # resolved in _create(): argument errors surface before any device work
+        self._ctx = context
         self._h = None
         self._elements_added = 0
         self._query_type = "min"
@@ -81,6 +82,8 @@ class CountMinSketch:
         self._create()
 
     def _create(self) -> None:
+        if self._ctx is None:
+            self._ctx = _native.default_context(self._ctx_arg[1])
         if self._h is not None:
             _native.lib().pb_cms_destroy(self._h)
         h = C.c_void_p()
@@ -183,17 +186,12 @@ class CountMinSketch:
     @staticmethod
     def _num_els_args(num_els, n):
         if isinstance(num_els, (int, np.integer)):
-            v = int(num_els)
-            if not INT64_T_MIN <= v <= INT64_T_MAX:
-                raise OverflowError("num_els does not fit in int64")
-            return None, v
+            # beyond int64 nothing changes any more: counters saturate at INT32_MAX and elements_added at INT64_MAX
+            return None, max(INT64_T_MIN, min(INT64_T_MAX, int(num_els)))
         arr = np.ascontiguousarray(num_els, dtype=np.int64)
         if arr.shape != (n,):
             raise ValueError("num_els must be an int or one int per key")
         return arr, 0
-
-    def _apply_elements_added(self, new_value: int) -> None:
-        self._elements_added = new_value
 
     def add_many(self, keys, num_els=1) -> None:
         """CountMinSketch.add (:257-288) for every key; num_els is an int or an int64 array (one per key)"""

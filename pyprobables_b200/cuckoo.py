@@ -56,7 +56,8 @@ class CuckooFilter:
         )
         if not ok:
             raise InitializationError("CuckooFilter: capacity, bucket_size, and max_swaps must be an integer greater than 0")
-        self._ctx = context if context is not None else _native.default_context(device)
+        self._ctx_arg = (context, device)  # resolved in _create(): argument errors surface before any device work
+        self._ctx = context
         self._h = None
         self._rng_seed = int(rng_seed)
         self._bucket_size = int(bucket_size)
@@ -107,6 +108,8 @@ class CuckooFilter:
             self._h = None
         if self._fingerprint_bits > 32:
             raise NotSupportedError("fingerprints wider than 32 bits do not fit the u32 slot format (cuckoo.py:402)")
+        if self._ctx is None:
+            self._ctx = _native.default_context(self._ctx_arg[1])
         h = C.c_void_p()
         _native.call("pb_cuckoo_create", self._ctx.handle, self._capacity, self._bucket_size, self._max_swaps,
                      self._fingerprint_bits, self._rng_seed, C.byref(h))

@@ -170,3 +170,54 @@ def test_shim_validation_matches_reference_messages(native):
     # host hash plugins (hashes_test.py:64-146 vectors)
     assert pb.hashes.default_md5("this is a test", 3)[0] == 12174049463882854484
     assert pb.hashes.default_sha256("this is a test", 1)[0] == 10244166640140130606
+
+
+def test_constructor_errors_come_before_device_work():
+    """argument validation needs no GPU: the reference's messages (bloom_test.py:395-473,
+    countminsketch_test.py:435-561, cuckoo_test.py:353-447) are raised even on a GPU-less machine"""
+    import pyprobables_b200 as pb
+
+    cases = [
+        (lambda: pb.BloomFilter(est_elements=100, false_positive_rate=1.1), pb.InitializationError,
+         "Bloom: false positive rate must be between 0.0 and 1.0"),
+        (lambda: pb.BloomFilter(est_elements=0, false_positive_rate=0.1), pb.InitializationError,
+         "Bloom: estimated elements must be greater than 0"),
+        (lambda: pb.BloomFilter(est_elements=100, false_positive_rate="1.1"), pb.InitializationError,
+         "Bloom: false positive rate must be between 0.0 and 1.0"),
+        (lambda: pb.BloomFilter(est_elements=[0], false_positive_rate=0.1), pb.InitializationError,
+         "Bloom: estimated elements must be greater than 0"),
+        (lambda: pb.BloomFilter(est_elements=10, false_positive_rate=0.999), pb.InitializationError,
+         "Bloom: Number hashes is zero; unusable parameters provided"),
+        (lambda: pb.BloomFilter(), pb.InitializationError, "Insufecient parameters to set up the Bloom Filter"),
+        (lambda: pb.CountMinSketch(width=0, depth=5), pb.InitializationError, "CountMinSketch: width and depth must be greater than 0"),
+        (lambda: pb.CountMinSketch(width=10, depth=-1), pb.InitializationError, "CountMinSketch: width and depth must be greater than 0"),
+        (lambda: pb.CountMinSketch(confidence=-1, error_rate=0.1), pb.InitializationError,
+         "CountMinSketch: width and depth must be greater than 0"),
+        (lambda: pb.CountMinSketch(), pb.InitializationError, "Must provide one of the following to initialize the Count-Min Sketch:"),
+        (lambda: pb.CuckooFilter(capacity=0), pb.InitializationError,
+         "CuckooFilter: capacity, bucket_size, and max_swaps must be an integer greater than 0"),
+        (lambda: pb.CuckooFilter(bucket_size=0), pb.InitializationError,
+         "CuckooFilter: capacity, bucket_size, and max_swaps must be an integer greater than 0"),
+        (lambda: pb.CuckooFilter(max_swaps="a"), pb.InitializationError,
+         "CuckooFilter: capacity, bucket_size, and max_swaps must be an integer greater than 0"),
+        (lambda: pb.CuckooFilter(finger_size=5), ValueError, "CuckooFilter: fingerprint size must be between 1 and 4"),
+        (lambda: pb.CuckooFilter(filepath="/nonexistent/file.cko"), pb.InitializationError, "CuckooFilter: failed to load provided file"),
+    ]
+    for make, exc, msg in cases:
+        with pytest.raises(exc) as ei:
+            make()
+        assert str(ei.value).startswith(msg), (str(ei.value), msg)
+
+
+def test_shard_plan_is_window_aligned():
+    from pyprobables_b200.sharded import ShardPlan
+
+    for m, g in ((9585058424, 1), (19170116848, 2), (76680467392, 8), (143775874672, 8), (479252922, 2), (63, 4)):
+        p = ShardPlan.make(m, g)
+        assert p.shard_bits == p.windows_per_rank << p.window_log2
+        assert p.total_windows == p.windows_per_rank * g <= ShardPlan.MAX_WINDOWS
+        assert (p.total_windows << p.window_log2) >= m
+        assert sum(p.active_windows(r) for r in range(g)) == -(-m // (1 << p.window_log2))
+        for r in range(g):
+            lo, hi = p.bounds(r)
+            assert lo % (1 << p.window_log2) == 0 or lo == m
