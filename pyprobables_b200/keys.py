@@ -87,10 +87,14 @@ def _pack_sequence_wide(keys: Sequence) -> KeyBatch:
     return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, n, 0, 4, False, (data, offsets))
 
 
-def pack_keys(keys) -> KeyBatch:
+def pack_keys(keys, sync: bool = True) -> KeyBatch:
     """list/tuple of str|bytes, a single str|bytes (one key), a 2-D uint8 numpy array [n, L],
     a 2-D uint8 CUDA torch tensor [n, L] (zero-copy, device resident), an existing KeyBatch, or a
-    (packed uint8 buffer, uint64 offsets[n+1]) pair -> KeyBatch"""
+    (packed uint8 buffer, uint64 offsets[n+1]) pair -> KeyBatch.
+
+    sync: a CUDA tensor may still be being written on torch's current stream while the engine reads it on its
+    own stream; by default that stream is synchronized first.  Callers whose context runs ON torch's stream
+    (pyprobables_b200.sharded) pass sync=False and stay asynchronous."""
     if isinstance(keys, KeyBatch):
         return keys
     if isinstance(keys, (str, bytes, bytearray, memoryview)):
@@ -107,6 +111,8 @@ def pack_keys(keys) -> KeyBatch:
             raise TypeError("a torch key batch must be a 2-D uint8 tensor [n_keys, key_len]")
         t = keys.contiguous()
         if t.is_cuda:
+            if sync:
+                torch.cuda.current_stream(t.device).synchronize()
             return KeyBatch(t.data_ptr(), None, t.shape[0], t.shape[1], 1, True, (t,))
         return KeyBatch(t.data_ptr(), None, t.shape[0], t.shape[1], 1, False, (t,))
     if isinstance(keys, tuple) and len(keys) == 2 and isinstance(keys[0], np.ndarray) and isinstance(keys[1], np.ndarray):

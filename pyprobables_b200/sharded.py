@@ -300,7 +300,7 @@ class ShardedBloomFilter:
             self._ensure_buffers(max(hi - lo, 1), worst_case)
             self._counts.zero_()
             if hi > lo:
-                kb = pack_keys(t[lo:hi])
+                kb = pack_keys(t[lo:hi], sync=False)
                 _native.call("pb_bloom_route_keys", self._ctx.handle, kb.ref(), self._m, self._k, self.plan.shard_bits,
                              self.world, C.c_void_p(self._send.data_ptr()), self._slot, C.c_void_p(self._counts.data_ptr()))
             counts = self._counts[: self.world].clone()
@@ -367,7 +367,7 @@ class ShardedBloomFilter:
             h = ci & 1
             lo = min(ci * self.chunk_keys, n)
             hi = min(lo + self.chunk_keys, n)
-            kb = pack_keys(t[lo:hi]) if hi > lo else pack_keys(t[:0])
+            kb = pack_keys(t[lo:hi], sync=False) if hi > lo else pack_keys(t[:0], sync=False)
             with torch.cuda.stream(self._s_part):
                 if ci >= 2:
                     self._s_part.wait_event(b["ev_comm"][h])  # the all-to-all that read this send half is done
@@ -451,7 +451,7 @@ class ShardedBloomFilter:
         for ci in range(n_chunks):
             lo = min(ci * self.chunk_keys, n)
             hi = min(lo + self.chunk_keys, n)
-            kb = pack_keys(t[lo:hi]) if hi > lo else pack_keys(t[:0])
+            kb = pack_keys(t[lo:hi], sync=False) if hi > lo else pack_keys(t[:0], sync=False)
             _native.call("pb_p2p_partition_send", b["h"], kb.ref(), self._m, self._k, plan.window_log2,
                          C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
             _native.call("pb_p2p_apply", b["h"], self._h, act, plan.window_log2)
@@ -495,7 +495,7 @@ class ShardedBloomFilter:
             return
         for r in range(self.world):
             if sizes[r]:
-                _native.call("pb_bloom_add_keys", self._h, pack_keys(allk[r, : sizes[r]]).ref())
+                _native.call("pb_bloom_add_keys", self._h, pack_keys(allk[r, : sizes[r]], sync=False).ref())
         self._ctx.synchronize()
 
     def check_many(self, keys):
@@ -517,7 +517,7 @@ class ShardedBloomFilter:
         if self._h is not None:
             for r in range(self.world):
                 if sizes[r]:
-                    _native.call("pb_bloom_check_keys", self._h, pack_keys(allk[r, : sizes[r]]).ref(),
+                    _native.call("pb_bloom_check_keys", self._h, pack_keys(allk[r, : sizes[r]], sync=False).ref(),
                                  C.c_void_p(partial[r].data_ptr()), 1)
             self._ctx.synchronize()
         dist.all_reduce(partial, op=dist.ReduceOp.MIN, group=self.group)
