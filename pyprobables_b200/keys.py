@@ -36,36 +36,62 @@ def _is_torch_tensor(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
+def _finish(data: np.ndarray, lens: np.ndarray, sym_width: int) -> KeyBatch:
+    n = lens.size
+    if sym_width == 1 and n and lens[0] > 0 and (lens == lens[0]).all():
+        # equal-length byte keys: the fixed-stride layout (16-byte keys take the register fast path)
+        return KeyBatch(data.ctypes.data, None, n, int(lens[0]), sym_width, False, (data,))
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, n, 0, sym_width, False, (data, offsets))
+
+
 def _pack_sequence(keys: Sequence) -> KeyBatch:
+    """Packs a list of keys.  The two homogeneous cases -- all bytes-like, all str -- are joined in C (one
+    `join`, one `encode`), which is what keeps Python out of the way of the GPU; mixed lists take the
+    per-element path."""
+    n = len(keys)
+    if n == 0:
+        return _finish(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint64), 1)
+    first = keys[0]
+    try:
+        if isinstance(first, (bytes, bytearray, memoryview)):
+            joined = b"".join(keys)  # TypeError if a str hides in the list
+            lens = np.fromiter(map(len, keys), dtype=np.uint64, count=n)
+            if int(lens.sum()) == len(joined):  # (a memoryview of wider items would report items, not bytes)
+                return _finish(np.frombuffer(joined, dtype=np.uint8), lens, 1)
+        elif isinstance(first, str):
+            text = "".join(keys)  # TypeError if a bytes object hides in the list
+            lens = np.fromiter(map(len, keys), dtype=np.uint64, count=n)  # code points = symbols (hashes.py:98)
+            if text.isascii():
+                return _finish(np.frombuffer(text.encode("ascii"), dtype=np.uint8), lens, 1)
+            try:
+                return _finish(np.frombuffer(text.encode("latin-1"), dtype=np.uint8), lens, 1)
+            except UnicodeEncodeError:
+                data = np.frombuffer(text.encode("utf-32-le", "surrogatepass"), dtype="<u4")
+                return _finish(data, lens, 4)
+    except TypeError:
+        pass
+    return _pack_sequence_mixed(keys)
+
+
+def _pack_sequence_mixed(keys: Sequence) -> KeyBatch:
     n = len(keys)
     lens = np.empty(n, dtype=np.uint64)
     parts: list[bytes] = []
-    wide = False
     for i, k in enumerate(keys):
         if isinstance(k, str):
-            if k.isascii():
-                b = k.encode("ascii")
-            else:
-                try:
-                    b = k.encode("latin-1")
-                except UnicodeEncodeError:
-                    wide = True
-                    break
+            try:
+                b = k.encode("latin-1")
+            except UnicodeEncodeError:
+                return _pack_sequence_wide(keys)
         elif isinstance(k, (bytes, bytearray, memoryview)):
             b = bytes(k)
         else:
             raise TypeError(f"keys must be str or bytes-like, not {type(k).__name__}")
         parts.append(b)
         lens[i] = len(b)
-    if wide:
-        return _pack_sequence_wide(keys)
-    offsets = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(lens, out=offsets[1:])
-    data = np.frombuffer(b"".join(parts), dtype=np.uint8)
-    if n and (lens == lens[0]).all() and lens[0] > 0:
-        # equal-length keys: the fixed-stride layout (16-byte keys take the register fast path)
-        return KeyBatch(data.ctypes.data, None, n, int(lens[0]), 1, False, (data,))
-    return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, n, 0, 1, False, (data, offsets))
+    return _finish(np.frombuffer(b"".join(parts), dtype=np.uint8), lens, 1)
 
 
 def _pack_sequence_wide(keys: Sequence) -> KeyBatch:
@@ -81,10 +107,8 @@ def _pack_sequence_wide(keys: Sequence) -> KeyBatch:
             raise TypeError(f"keys must be str or bytes-like, not {type(k).__name__}")
         parts.append(a)
         lens[i] = a.size
-    offsets = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(lens, out=offsets[1:])
     data = np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0, dtype="<u4"), dtype="<u4")
-    return KeyBatch(data.ctypes.data if data.size else None, offsets.ctypes.data, n, 0, 4, False, (data, offsets))
+    return _finish(data, lens, 4)
 
 
 def pack_keys(keys, sync: bool = True) -> KeyBatch:
