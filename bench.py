@@ -401,9 +401,46 @@ def run_ours(args) -> None:
                    "keys_per_step": n_e, "api": "BloomFilter.add_many(uint8[n,16] pinned host array) + number-of-bits-set read back",
                    "bits_set": int(bits)}
             _native.call("pb_host_free", hp)
-        elif world > 1:
-            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "note": "end-to-end from host buffers is measured at N=1; multi-GPU steps start from device-resident keys"}
+        elif world > 1 and not args.no_e2e:
+            # every rank: pinned host keys -> H2D -> sharded insert (collective) -> read back its shard's popcount.
+            # All ranks first agree that the buffers exist, so nobody is left alone inside a collective.
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+            n_e = min(args.e2e_keys, n_keys)
+            host = dbuf = None
+            try:
+                host = torch.empty((n_e, 16), dtype=torch.uint8, pin_memory=True)
+                host.copy_(keys[:n_e])
+                dbuf = torch.empty((n_e, 16), dtype=torch.uint8, device=dev)
+                ready = 1
+            except Exception as ex:  # noqa: BLE001
+                ready = 0
+                e2e["note"] = f"host staging failed on rank {rank}: {str(ex)[:120]}"
+            flag = torch.tensor([ready], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                try:
+                    def e2e_step():
+                        filt.clear()
+                        dbuf.copy_(host, non_blocking=True)  # H2D of the step's keys on the engine's stream
+                        filt.add_many(dbuf)
+                        return filt.popcount_local()         # D2H of the step's result
+
+                    e2e_step()
+                    barrier()
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps):
+                        bits = e2e_step()
+                    barrier()
+                    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                    e2e.update(value=n_e * world * args.steps / float(dt.item()), h2d_bytes_per_step=n_e * 16 * world,
+                               d2h_bytes_per_step=8 * world, keys_per_step=n_e * world,
+                               api="ShardedBloomFilter.add_many per rank from a pinned host array + shard popcount read back",
+                               bits_set_rank0_shard=int(bits))
+                except Exception as ex:  # noqa: BLE001
+                    e2e["note"] = f"end-to-end leg failed: {str(ex)[:160]}"
+            elif "note" not in e2e:
+                e2e["note"] = "host staging failed on another rank"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
