@@ -71,6 +71,12 @@ def lib():
         L.orc_bloom_check_hashes.argtypes = [vp, u64, u32, vp, u64, vp]
         L.orc_popcount.restype = u64
         L.orc_popcount.argtypes = [vp, u64]
+        L.orc_cbloom_add.restype = u64
+        L.orc_cbloom_add.argtypes = [vp, u64, u32, C.POINTER(u64), KP, u64, vp]
+        L.orc_cbloom_check.restype = None
+        L.orc_cbloom_check.argtypes = [vp, u64, u32, KP, vp]
+        L.orc_cbloom_remove.restype = None
+        L.orc_cbloom_remove.argtypes = [vp, u64, u32, C.POINTER(i64), KP, u64, vp]
         L.orc_cms_add.restype = u64
         L.orc_cms_add.argtypes = [vp, u32, u32, C.POINTER(i64), KP, vp, i64, i32, vp]
         L.orc_cms_check.restype = None
@@ -222,6 +228,36 @@ class Bloom:
 
     def popcount(self) -> int:
         return lib().orc_popcount(self.bloom.ctypes.data, self.bloom.size)
+
+
+class CountingBloom:
+    """probables/blooms/countingbloom.py:125-208 on a numpy uint32 array (one counter per 'bit', so the array
+    length equals number_bits, countingbloom.py:37)"""
+
+    def __init__(self, num_bits: int, k: int):
+        self.num_bits, self.k = num_bits, k
+        self.bloom = np.zeros(num_bits, dtype=np.uint32)
+        self.elements_added = 0
+
+    def add(self, keys: Keys, num_els: int = 1) -> np.ndarray:
+        ea = C.c_uint64(self.elements_added)
+        post = np.empty(keys.n, dtype=np.uint64)
+        clamped = lib().orc_cbloom_add(self.bloom.ctypes.data, self.num_bits, self.k, C.byref(ea), keys.ref(), num_els, post.ctypes.data)
+        assert clamped == 0, "reference would raise OverflowError (array('I') past UINT32_MAX)"
+        self.elements_added = ea.value
+        return post
+
+    def check(self, keys: Keys) -> np.ndarray:
+        out = np.empty(keys.n, dtype=np.uint64)
+        lib().orc_cbloom_check(self.bloom.ctypes.data, self.num_bits, self.k, keys.ref(), out.ctypes.data)
+        return out
+
+    def remove(self, keys: Keys, num_els: int = 1) -> np.ndarray:
+        ea = C.c_int64(self.elements_added)
+        post = np.empty(keys.n, dtype=np.uint64)
+        lib().orc_cbloom_remove(self.bloom.ctypes.data, self.num_bits, self.k, C.byref(ea), keys.ref(), num_els, post.ctypes.data)
+        self.elements_added = ea.value
+        return post
 
 
 class CMS:

@@ -170,6 +170,87 @@ uint64_t orc_popcount(const uint8_t *buf, uint64_t nbytes) {
     return c;
 }
 
+/* ------------------------------------------------------------------ Counting Bloom ("next" row) */
+
+#define ORC_U32_MAX 4294967295ULL
+
+/* probables/blooms/countingbloom.py:135-155, sequential over the batch.  The k counters are read first
+ * (vals = bloom[idx] + n), then updated one by one with `bloom[idx] += n` -- so an index hit by two of a key's
+ * hashes is incremented twice although both snapshots saw the old value (the reference's own NOTE at :143).
+ * post_add (optional) receives min(vals) per key (:155).  A counter pushed past UINT32_MAX by the double
+ * increment would raise OverflowError in the reference's array('I'); it is clamped here and counted in the
+ * return value so tests can assert it never happens. */
+uint64_t orc_cbloom_add(uint32_t *bloom, uint64_t length, uint32_t k, uint64_t *elements_added, const orc_keys *keys,
+                        uint64_t num_els, uint64_t *post_add) {
+    uint64_t clamped = 0, idx[64], vals[64];
+    for (uint64_t i = 0; i < keys->n; ++i) {
+        uint64_t beg, len;
+        key_span(keys, i, &beg, &len);
+        const uint32_t kk = k < 64 ? k : 64;
+        for (uint32_t s = 0; s < kk; ++s) {
+            idx[s] = fnv1a_syms(keys, beg, len, s) % length; /* :145 */
+            vals[s] = (uint64_t)bloom[idx[s]] + num_els;     /* :146 */
+        }
+        uint64_t mn = ~0ULL;
+        for (uint32_t s = 0; s < kk; ++s) {
+            if (vals[s] > ORC_U32_MAX) { /* :149-151 */
+                bloom[idx[s]] = (uint32_t)ORC_U32_MAX;
+                vals[s] = ORC_U32_MAX;
+            } else { /* :153 */
+                uint64_t v = (uint64_t)bloom[idx[s]] + num_els;
+                if (v > ORC_U32_MAX) { v = ORC_U32_MAX; ++clamped; }
+                bloom[idx[s]] = (uint32_t)v;
+            }
+            if (vals[s] < mn) mn = vals[s];
+        }
+        /* :154 (UINT64 saturation) */
+        *elements_added = (*elements_added > ~0ULL - num_els) ? ~0ULL : *elements_added + num_els;
+        if (post_add) post_add[i] = mn;
+    }
+    return clamped;
+}
+
+/* countingbloom.py:157-175: min over the k counters */
+void orc_cbloom_check(const uint32_t *bloom, uint64_t length, uint32_t k, const orc_keys *keys, uint64_t *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)keys->n; ++i) {
+        uint64_t beg, len, mn = ~0ULL;
+        key_span(keys, (uint64_t)i, &beg, &len);
+        for (uint32_t s = 0; s < k; ++s) {
+            uint64_t v = bloom[fnv1a_syms(keys, beg, len, s) % length];
+            if (v < mn) mn = v;
+        }
+        out[i] = mn;
+    }
+}
+
+/* countingbloom.py:177-208, sequential: remove min(num_els, current minimum) from every counter of the key that is
+ * not saturated; post (optional) receives what remove() returns. */
+void orc_cbloom_remove(uint32_t *bloom, uint64_t length, uint32_t k, int64_t *elements_added, const orc_keys *keys,
+                       uint64_t num_els, uint64_t *post) {
+    uint64_t idx[64];
+    for (uint64_t i = 0; i < keys->n; ++i) {
+        uint64_t beg, len, mn = ~0ULL;
+        key_span(keys, i, &beg, &len);
+        const uint32_t kk = k < 64 ? k : 64;
+        for (uint32_t s = 0; s < kk; ++s) {
+            idx[s] = fnv1a_syms(keys, beg, len, s) % length;
+            if (bloom[idx[s]] < mn) mn = bloom[idx[s]];
+        }
+        uint64_t ret;
+        if (mn == ORC_U32_MAX) ret = ORC_U32_MAX;      /* :196-197 */
+        else if (mn == 0) ret = 0;                     /* :198-199 */
+        else {
+            const uint64_t take = mn > num_els ? num_els : mn; /* :201 */
+            for (uint32_t s = 0; s < kk; ++s)
+                if (bloom[idx[s]] < ORC_U32_MAX) bloom[idx[s]] -= (uint32_t)take; /* :202-204 (twice on a shared index) */
+            *elements_added -= (int64_t)take;
+            ret = mn - take;
+        }
+        if (post) post[i] = ret;
+    }
+}
+
 /* ------------------------------------------------------------------ Count-Min */
 
 #define ORC_I32_MAX 2147483647LL

@@ -102,3 +102,26 @@ def test_cuckoo_random(ref, orc, capacity, bucket, fp_bytes):
     assert o.fingerprints().tolist() == stored
     probes = keys[:50] + _random_keys(rng, 300)
     assert o.check(orc.pack(probes)).tolist() == [r.check(p) for p in probes]
+
+
+@pytest.mark.parametrize("est,fpr", [(20, 0.05), (300, 0.01), (2000, 0.2)])
+def test_counting_bloom_random(ref, orc, est, fpr):
+    """oracle head start for the next scope row (CountingBloomFilter, countingbloom.py:125-208), including the
+    double increment when two of a key's hashes share an index"""
+    rng = random.Random(est)
+    r = ref.CountingBloomFilter(est_elements=est, false_positive_rate=fpr)
+    o = orc.CountingBloom(r.number_bits, r.number_hashes)
+    pool = _random_keys(rng, max(est // 2, 10), unicode_share=0.1)
+    for _ in range(6):
+        batch = [rng.choice(pool) for _ in range(est)]
+        n = rng.choice([1, 1, 2, 5])
+        assert o.add(orc.pack(batch), n).tolist() == [r.add(k, n) for k in batch]
+        assert o.bloom.tolist() == list(r._bloom) and o.elements_added == r.elements_added
+        rem = [rng.choice(pool) for _ in range(est // 3)]
+        m = rng.choice([1, 3])
+        assert o.remove(orc.pack(rem), m).tolist() == [r.remove(k, m) for k in rem]
+        assert o.bloom.tolist() == list(r._bloom) and o.elements_added == r.elements_added
+    probes = pool + _random_keys(rng, 100)
+    assert o.check(orc.pack(probes)).tolist() == [r.check(p) for p in probes]
+    # export bytes: uint32 counters + the Bloom footer
+    assert o.bloom.tobytes() + struct.pack("QQf", est, o.elements_added, r.false_positive_rate) == bytes(r)
