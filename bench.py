@@ -152,6 +152,7 @@ def run_reference(args) -> None:
         kind = "port"
         from oracle import oracle as orc
 
+        orc.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
         fpr32, k, m, _ = orc.bloom_params(est, FPR)
         ob = orc.Bloom(m, k)
         sample = max(sample, 20_000_000)
@@ -180,6 +181,7 @@ def run_reference(args) -> None:
         try:
             from oracle import oracle as orc
 
+            orc.set_threads(os.cpu_count() or 1)
             _, ok, om, _ = orc.bloom_params(est, FPR)
             ob = orc.Bloom(om, ok)
             ns = 20_000_000
@@ -200,6 +202,7 @@ def cpu_baseline_port(m: int, k: int, seconds: float = 12.0) -> dict:
     """the oracle (C port of the reference algorithm) on all host cores, bounded sample of the same workload"""
     from oracle import oracle as orc
 
+    orc.set_threads(os.cpu_count() or 1)
     ob = orc.Bloom(m, k)
     probe = 4_000_000
     t0 = time.perf_counter()

@@ -152,6 +152,7 @@ _SPECIAL = {"pb_version": (C.c_int, []), "pb_last_error": (_cp, [])}
 _TEST_HOOKS = {
     "pbt_fnv1a": (_u64, [_vp, _u64, _u64]),
     "pbt_fastmod": (_u64, [_u64, _u64]),
+    "pbt_mod_fast33": (_u64, [_u64, _u64]),
     "pbt_cuckoo_info": (None, [_u64, _u32, _u64, _P(_u32), _P(_u64), _P(_u64)]),
     "pbt_sm64": (_u64, [_u64]),
     "pbt_pick_group": (C.c_int, [_u32]),

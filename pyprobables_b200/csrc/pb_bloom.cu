@@ -221,95 +221,6 @@ __global__ void __launch_bounds__(256) popcount_kernel(const uint4 *__restrict__
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
-// ---------------------------------------------------------------- partitioned insert
-constexpr int kMaxWindows = 1024;
-
-struct PartDev {
-    uint32_t *stage;              // n_windows * cap local indices
-    unsigned long long *cursors;  // n_windows
-    uint64_t cap;                 // per-window capacity (items, multiple of 4)
-    uint32_t window_log2;         // bits per window = 1 << window_log2 (<= 32)
-    uint32_t n_windows;
-};
-
-// pass 1: hash, bin by window, write window-local bit indices
-template <int KG, int NG>
-__global__ void __launch_bounds__(256) bloom_part_fixed16(const uint4 *__restrict__ keys, uint64_t n, BloomDev b, PartDev p) {
-    __shared__ uint32_t hist[kMaxWindows];
-    __shared__ unsigned long long base[kMaxWindows];
-    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
-    const uint32_t local_mask = p.window_log2 >= 32 ? 0xFFFFFFFFu : ((1u << p.window_log2) - 1u);
-    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (uint32_t w = threadIdx.x; w < p.n_windows; w += blockDim.x) hist[w] = 0;
-        __syncthreads();
-        const uint64_t i = tile * blockDim.x + threadIdx.x;
-        uint64_t idx[NG][KG];
-        uint32_t rank[NG][KG];
-        if (i < n) {
-            const uint4 w = __ldcs(keys + i);
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                uint64_t h[KG];
-                fnv_group_16<KG>(w, g * KG, h);
-#pragma unroll
-                for (int j = 0; j < KG; ++j) {
-                    if ((uint32_t)(g * KG + j) < b.k) {
-                        idx[g][j] = fastmod(h[j], b.fm);
-                        rank[g][j] = atomicAdd(&hist[(uint32_t)(idx[g][j] >> p.window_log2)], 1u);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (uint32_t w = threadIdx.x; w < p.n_windows; w += blockDim.x)
-            base[w] = hist[w] ? atomicAdd(p.cursors + w, (unsigned long long)hist[w]) : 0ull;
-        __syncthreads();
-        if (i < n) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-#pragma unroll
-                for (int j = 0; j < KG; ++j) {
-                    if ((uint32_t)(g * KG + j) < b.k) {
-                        const uint32_t w = (uint32_t)(idx[g][j] >> p.window_log2);
-                        const unsigned long long pos = base[w] + rank[g][j];
-                        if (pos < p.cap) {
-                            __stcs(p.stage + (uint64_t)w * p.cap + pos, (uint32_t)idx[g][j] & local_mask);
-                        } else {  // window overflow (skewed keys): apply straight to the bitmap
-                            atomicOr(b.words + (idx[g][j] >> 5), 1u << (uint32_t)(idx[g][j] & 31));
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// pass 2: windows in launch order; each window's bitmap slice stays in L2 while its list streams by
-__global__ void __launch_bounds__(256) bloom_apply_windows(BloomDev b, PartDev p, uint32_t ctas_per_window) {
-    const uint32_t w = blockIdx.x / ctas_per_window;
-    const uint32_t c = blockIdx.x % ctas_per_window;
-    unsigned long long cnt = p.cursors[w];
-    if (cnt > p.cap) cnt = p.cap;
-    uint32_t *words = b.words + ((uint64_t)w << (p.window_log2 - 5));
-    const uint32_t *list = p.stage + (uint64_t)w * p.cap;
-    const uint64_t n4 = cnt >> 2;
-    const uint4 *list4 = reinterpret_cast<const uint4 *>(list);
-    for (uint64_t i = (uint64_t)c * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)ctas_per_window * blockDim.x) {
-        const uint4 v = __ldcs(list4 + i);
-        atomicOr(words + (v.x >> 5), 1u << (v.x & 31));
-        atomicOr(words + (v.y >> 5), 1u << (v.y & 31));
-        atomicOr(words + (v.z >> 5), 1u << (v.z & 31));
-        atomicOr(words + (v.w >> 5), 1u << (v.w & 31));
-    }
-    if (c == 0) {
-        for (uint64_t i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t v = list[i];
-            atomicOr(words + (v >> 5), 1u << (v & 31));
-        }
-    }
-}
-
 // ---------------------------------------------------------------- multi-GPU routing
 // hash keys, find the owning shard of every bit index, append the (global) index to that shard's slot.
 template <int KG>
@@ -432,11 +343,10 @@ struct PartPlan {
     uint32_t n_windows = 0;
     uint64_t cap = 0;
     uint64_t chunk_keys = 0;
-    int kg = 0, ng = 0;
-    int version = 3;  // 1: bloom_part_fixed16 + bloom_apply_windows, 2/3: pb_bloom_part.cuh
+    int version = 4;  // 3: bloom_part3_fixed16 (round 1, 16-byte keys only), 4: bloom_part4 (any key layout)
     int halves = 1;   // 2: the staging is split in two so pass 2 of one chunk overlaps pass 1 of the next
     uint32_t quota = kQuota;
-    int grid = 0;     // CTAs of the pass-1 launch (the v2 staging slack depends on it)
+    int grid = 0;     // CTAs of the pass-1 launch (the staging slack depends on it)
 };
 
 // Decide whether (and how) a batch of n keys goes through the partitioned path.
@@ -444,7 +354,9 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     PartPlan pl;
     pb_ctx *ctx = b->ctx;
     const int64_t mode = ctx->bloom_insert_mode;
-    if (mode == 1 || !fixed16 || b->k > 16) return pl;
+    const int version = ctx->bloom_part_version == 3 ? 3 : 4;
+    if (mode == 1 || b->k > kMaxPartK) return pl;
+    if (!fixed16 && version == 3) return pl;
     if (b->lo_bit != 0 || b->hi_bit != b->num_bits) return pl;  // shards take routed indices instead
     const uint64_t l2 = ctx->l2_bytes ? ctx->l2_bytes : ((uint64_t)96 << 20);
     if (mode == 0) {
@@ -453,9 +365,8 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
         if (b->nbytes <= l2) return pl;
         if ((double)n * b->k * 64.0 < 4.0 * (double)b->nbytes) return pl;
     }
-    const int version = ctx->bloom_part_version == 1 ? 1 : (ctx->bloom_part_version == 2 ? 2 : 3);
-    const uint32_t wl_max = version >= 2 ? 31 : 32;
-    const uint64_t max_windows = version >= 2 ? (uint64_t)kMaxWindows2 : (uint64_t)kMaxWindows;
+    const uint32_t wl_max = 31;
+    const uint64_t max_windows = (uint64_t)kMaxWindows2;
     uint32_t wl = (uint32_t)ctx->bloom_window_log2_bits;
     if (wl > wl_max) wl = wl_max;
     while (((b->num_bits + ((1ull << wl) - 1)) >> wl) > max_windows && wl < wl_max) ++wl;
@@ -463,21 +374,21 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     if (nw > max_windows || wl < 5) return pl;
     uint64_t stage_items = (uint64_t)ctx->stage_bytes / 4;
     // overlap only pays when the batch needs more than one chunk anyway or is big enough to split in two
-    const int halves = (version >= 2 && ctx->bloom_overlap && n >= (1ull << 24)) ? 2 : 1;
+    const int halves = (ctx->bloom_overlap && n >= (1ull << 24)) ? 2 : 1;
     stage_items /= (uint64_t)halves;
-    if (version >= 2 && stage_items > 0xFFFFFFF0ull) stage_items = 0xFFFFFFF0ull;  // 32-bit entry numbers
+    if (stage_items > 0xFFFFFFF0ull) stage_items = 0xFFFFFFF0ull;  // 32-bit entry numbers
     uint64_t cap = (stage_items / nw) & ~(uint64_t)3;
     const double per_key_per_window = (double)b->k * (double)(1ull << wl) / (double)b->num_bits;  // <= k
-    const int grid = grid_for(ctx, n, 256, version >= 2 ? 4 : 6);
-    // room every window needs beyond its expected share: statistical slack + (v2) the partly used quotas
-    const double slack = 8192.0 + (version >= 2 ? (double)grid * (double)kQuota : 0.0);
+    const int grid = grid_for(ctx, n, 256, 4);
+    // room every window needs beyond its expected share: statistical slack + the partly used quotas
+    const double slack = 8192.0 + (double)grid * (double)kQuota;
     // shrink the staging to what this batch needs
     uint64_t need = (uint64_t)((double)n * std::min(per_key_per_window, (double)b->k) * 1.03 + slack);
     need = (need + 3) & ~(uint64_t)3;
     if (need < cap) cap = need;
     if ((double)cap < 2.0 * slack + 16384.0) return pl;
     uint64_t chunk = (uint64_t)(((double)cap - slack) / 1.03 / std::min(per_key_per_window, (double)b->k));
-    if (version >= 2) chunk = std::min<uint64_t>(chunk, (0xF0000000ull - (uint64_t)grid * kQuota) / b->k);  // u32 cursors
+    chunk = std::min<uint64_t>(chunk, (0xF0000000ull - (uint64_t)grid * kQuota) / b->k);  // u32 cursors
     if (halves == 2) chunk = std::min<uint64_t>(chunk, (n + 3) / 4);  // at least four chunks to pipeline
     pl.halves = halves;
     pl.quota = pick_quota(chunk, b->k, (uint32_t)nw, grid);  // <= kQuota, which the slack above allowed for
@@ -489,20 +400,35 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     pl.n_windows = (uint32_t)nw;
     pl.cap = cap;
     pl.chunk_keys = chunk;
-    if (b->k <= 8) {
-        pl.kg = (int)b->k;
-        pl.ng = 1;
-    } else {
-        pl.kg = (int)((b->k + 1) / 2);
-        pl.ng = 2;
-    }
     return pl;
 }
 
-template <int KG, int NG>
-static int launch_part(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd, const PartDev &pd) {
+// pass 1 of the round-1 generation (16-byte keys only): kept selectable ("bloom_part_version" = 3) as a cross-check
+static int launch_part3_any(uint32_t k, bool big_tile, int grid, cudaStream_t stream, const uint4 *k4, uint64_t n, const Part2Dev &pd) {
+    const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
+    switch (ng * 100 + kg) {
+#define PB_P3(KG, NG) \
+    case NG * 100 + KG: launch_part3<KG, NG, false>(big_tile, grid, stream, k4, n, pd, P2PDst{}); return PB_OK;
+        PB_P3(1, 1) PB_P3(2, 1) PB_P3(3, 1) PB_P3(4, 1) PB_P3(5, 1) PB_P3(6, 1) PB_P3(7, 1) PB_P3(8, 1)
+        PB_P3(5, 2) PB_P3(6, 2) PB_P3(7, 2) PB_P3(8, 2)
+#undef PB_P3
+        default: set_error("internal: no partition kernel for k=%u", k); return PB_ERR_UNSUPPORTED;
+    }
+}
+
+// Pass 1 of a key batch into stage[n_windows][cap] / cursors (zeroed here); any key layout for version 4.
+static int launch_partition(pb_ctx *ctx, int version, bool big_tile, int grid, const DevKeys &dk, const Part2Dev &pd) {
     launch_begin(ctx);
-    bloom_part_fixed16<KG, NG><<<grid_for(ctx, dk.n, 256, 6), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, bd, pd);
+    if (version == 3) {
+        PB_REQUIRE(is_fixed16(dk), "the round-1 partition kernel takes 16-byte keys");
+        PB_TRY(launch_part3_any(pd.k, big_tile, grid, ctx->stream, (const uint4 *)dk.data, dk.n, pd));
+    } else {
+        cudaError_t e = launch_part4(pd.k, big_tile, grid, ctx->stream, dk, pd);
+        if (e != cudaSuccess) {
+            set_error("launch of bloom_part4 (k=%u) failed: %s", pd.k, cudaGetErrorString(e));
+            return PB_ERR_CUDA;
+        }
+    }
     return check_launch(ctx, "bloom_part");
 }
 
@@ -520,24 +446,22 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
     pb_bloom *b = a->b;
     const BloomDev bd = dev_view(b);
     int st = PB_OK;
-    if (a->plan.use && a->plan.version >= 2 && is_fixed16(dk)) {
+    if (a->plan.use && (a->plan.version == 4 || is_fixed16(dk))) {
         const PartPlan &pl = a->plan;
         const bool overlap = pl.halves == 2;
         const int half = overlap ? (int)(a->chunk_no++ & 1) : 0;
         const size_t half_entries = (size_t)pl.n_windows * pl.cap;
         PB_TRY(scratch_reserve(ctx, ctx->part_stage, half_entries * 4 * (size_t)pl.halves));
-        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, (size_t)kMaxWindows * 8));
+        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, (size_t)kMaxWindows2 * 4 * 2));
         Part2Dev pd;
         pd.stage = (uint32_t *)ctx->part_stage.p + (size_t)half * half_entries;
         pd.cursors = (unsigned int *)ctx->part_cursors.p + (size_t)half * kMaxWindows2;
         pd.words = b->words;
-        pd.m = b->num_bits;
-        pd.recip = b->fm.recip;
+        part_set_modulus(pd, b->num_bits);
         pd.cap = (uint32_t)pl.cap;
         pd.window_log2 = pl.window_log2;
         pd.n_windows = pl.n_windows;
         pd.k = b->k;
-        pd.recip_fits32 = b->num_bits > (1ull << 32) ? 1u : 0u;
         pd.quota = pl.quota;
         pd.ovf_list = nullptr;
         pd.ovf_count = nullptr;
@@ -546,33 +470,8 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
         if (overlap && ctx->apply_pending[half]) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[half], 0));
         PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 4, ctx->stream));
         const int grid = std::min(pl.grid, grid_for(ctx, dk.n, 256, 4));
-        const bool big_tile = part_big_tile(ctx, pl.n_windows) && pl.version == 3 && grid >= 2;
-        const uint4 *k4 = (const uint4 *)dk.data;
-        launch_begin(ctx);
-        switch (pl.ng * 100 + pl.kg) {
-#define PB_P2(KG, NG)                                                                                   \
-    do {                                                                                                \
-        if (pl.version == 2) bloom_part2_fixed16<KG, NG><<<grid, 256, 0, ctx->stream>>>(k4, dk.n, pd);    \
-        else launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, dk.n, pd, P2PDst{});                           \
-    } while (0)
-            case 101: PB_P2(1, 1); break;
-            case 102: PB_P2(2, 1); break;
-            case 103: PB_P2(3, 1); break;
-            case 104: PB_P2(4, 1); break;
-            case 105: PB_P2(5, 1); break;
-            case 106: PB_P2(6, 1); break;
-            case 107: PB_P2(7, 1); break;
-            case 108: PB_P2(8, 1); break;
-            case 205: PB_P2(5, 2); break;
-            case 206: PB_P2(6, 2); break;
-            case 207: PB_P2(7, 2); break;
-            case 208: PB_P2(8, 2); break;
-#undef PB_P2
-            default:
-                set_error("internal: no partition kernel for k=%u", b->k);
-                return PB_ERR_UNSUPPORTED;
-        }
-        PB_TRY(check_launch(ctx, "bloom_part"));
+        const bool big_tile = part_big_tile(ctx, pl.n_windows) && grid >= 2;
+        PB_TRY(launch_partition(ctx, pl.version, big_tile, grid, dk, pd));
         const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
         cudaStream_t s2 = ctx->stream;
         if (overlap) {
@@ -589,41 +488,6 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
             a->overlapped = true;
         }
         return PB_OK;
-    }
-    if (a->plan.use && is_fixed16(dk)) {
-        const PartPlan &pl = a->plan;
-        PB_TRY(scratch_reserve(ctx, ctx->part_stage, (size_t)pl.n_windows * pl.cap * 4));
-        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, (size_t)kMaxWindows * 8));
-        PartDev pd;
-        pd.stage = (uint32_t *)ctx->part_stage.p;
-        pd.cursors = (unsigned long long *)ctx->part_cursors.p;
-        pd.cap = pl.cap;
-        pd.window_log2 = pl.window_log2;
-        pd.n_windows = pl.n_windows;
-        PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 8, ctx->stream));
-        const int code = pl.ng * 100 + pl.kg;
-        switch (code) {
-            case 101: st = launch_part<1, 1>(ctx, dk, bd, pd); break;
-            case 102: st = launch_part<2, 1>(ctx, dk, bd, pd); break;
-            case 103: st = launch_part<3, 1>(ctx, dk, bd, pd); break;
-            case 104: st = launch_part<4, 1>(ctx, dk, bd, pd); break;
-            case 105: st = launch_part<5, 1>(ctx, dk, bd, pd); break;
-            case 106: st = launch_part<6, 1>(ctx, dk, bd, pd); break;
-            case 107: st = launch_part<7, 1>(ctx, dk, bd, pd); break;
-            case 108: st = launch_part<8, 1>(ctx, dk, bd, pd); break;
-            case 205: st = launch_part<5, 2>(ctx, dk, bd, pd); break;
-            case 206: st = launch_part<6, 2>(ctx, dk, bd, pd); break;
-            case 207: st = launch_part<7, 2>(ctx, dk, bd, pd); break;
-            case 208: st = launch_part<8, 2>(ctx, dk, bd, pd); break;
-            default:
-                set_error("internal: no partition kernel for k=%u", b->k);
-                return PB_ERR_UNSUPPORTED;
-        }
-        PB_TRY(st);
-        const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
-        launch_begin(ctx);
-        bloom_apply_windows<<<pl.n_windows * cpw, 256, 0, ctx->stream>>>(bd, pd, cpw);
-        return check_launch(ctx, "bloom_apply_windows");
     }
     const int kg = pick_group(b->k);
 #define CALL(K) launch_add_direct<K>(ctx, dk, bd)
@@ -934,43 +798,26 @@ int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits,
     pd.stage = stage_dev;
     pd.cursors = cursors_dev;
     pd.words = nullptr;
-    pd.m = num_bits;
-    pd.recip = make_fastmod(num_bits).recip;
+    part_set_modulus(pd, num_bits);
     pd.cap = cap;
     pd.window_log2 = window_log2;
     pd.n_windows = n_windows;
     pd.k = k;
-    pd.recip_fits32 = num_bits > (1ull << 32) ? 1u : 0u;
     pd.quota = pick_quota(keys->n, k, n_windows, grid_for(ctx, keys->n, 256, 4));
     pd.ovf_list = ovf_list_dev;
     pd.ovf_count = (unsigned long long *)ovf_count_dev;
     pd.ovf_cap = ovf_cap;
     const int grid = grid_for(ctx, keys->n, 256, 4);
     const bool big_tile = part_big_tile(ctx, n_windows) && grid >= 2;
-    const uint4 *k4 = (const uint4 *)keys->data;
-    const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
-    launch_begin(ctx);
-    switch (ng * 100 + kg) {
-#define PB_P3(KG, NG)                                                                                                   \
-    do {                                                                                                                \
-        launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, keys->n, pd, P2PDst{});                            \
-    } while (0)
-        case 101: PB_P3(1, 1); break;
-        case 102: PB_P3(2, 1); break;
-        case 103: PB_P3(3, 1); break;
-        case 104: PB_P3(4, 1); break;
-        case 105: PB_P3(5, 1); break;
-        case 106: PB_P3(6, 1); break;
-        case 107: PB_P3(7, 1); break;
-        case 108: PB_P3(8, 1); break;
-        case 205: PB_P3(5, 2); break;
-        case 206: PB_P3(6, 2); break;
-        case 207: PB_P3(7, 2); break;
-        case 208: PB_P3(8, 2); break;
-#undef PB_P3
-        default: set_error("internal: no partition kernel for k=%u", k); return PB_ERR_UNSUPPORTED;
-    }
-    return check_launch(ctx, "bloom_part");
+    DevKeys dk;
+    dk.data = (const uint8_t *)keys->data;
+    dk.offsets = nullptr;
+    dk.n = keys->n;
+    dk.stride = 16;
+    dk.sym_width = 1;
+    dk.base_symbol = 0;
+    dk.total_bytes = keys->n * 16;
+    return launch_partition(ctx, ctx->bloom_part_version == 3 ? 3 : 4, big_tile, grid, dk, pd);
 }
 
 // Slack a window list needs beyond its expected share for a pb_bloom_partition_keys call of n keys

@@ -37,6 +37,10 @@ struct Part2Dev {
     uint32_t n_windows;
     uint32_t k;
     uint32_t recip_fits32;   // m > 2^32
+    // m >= 2^33 (every BASELINE-size filter): quotient < 2^31, so h - q*m is one signed mad.wide + one mad.lo
+    uint32_t fast33;
+    int32_t m_lo_s;          // low word of m read as a signed number
+    uint32_t m_hi_adj;       // high word of m, plus one when the low word's sign bit is set
     uint32_t quota;          // list entries a CTA reserves per window and refill (<= kQuota)
     // multi-GPU routing: the bitmap of most windows lives on another GPU, so an index that does not fit its
     // window list cannot fall back to a local RED; it goes to this list of global bit indices instead
@@ -63,6 +67,33 @@ __device__ __forceinline__ uint64_t mod_big(uint64_t h, uint64_t m, uint32_t r32
     return r >= m ? r - m : r;
 }
 
+// modulus-derived fields of Part2Dev (host)
+inline void part_set_modulus(Part2Dev &pd, uint64_t m) {
+    pd.m = m;
+    pd.recip = make_fastmod(m).recip;
+    pd.recip_fits32 = m > (1ull << 32) ? 1u : 0u;
+    pd.fast33 = m >= (1ull << 33) ? 1u : 0u;
+    pd.m_lo_s = (int32_t)(uint32_t)m;
+    pd.m_hi_adj = (uint32_t)(m >> 32) + (uint32_t)((m >> 31) & 1u);
+}
+
+// exact h % m for m >= 2^33.  R = floor(2^64/m) < 2^31; q = floor(h*R / 2^64) is floor(h/m) or one less and < 2^31,
+// so -q is a signed 32-bit number: r = h - q*m = h + (-q)*m_lo_s (signed 32x32+64) with the high word corrected by
+// (-q)*m_hi_adj, then one conditional subtract.  Host twin (same steps in portable C): pbt_mod_fast33 in pb_ctx.cu.
+__device__ __forceinline__ uint64_t mod_fast33(uint64_t h, const Part2Dev &p) {
+    const uint32_t r32 = (uint32_t)p.recip;
+    const uint32_t t_hi = __umulhi((uint32_t)h, r32);
+    uint64_t u;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(u) : "r"((uint32_t)(h >> 32)), "r"(r32), "l"((uint64_t)t_hi));
+    const int32_t nq = -(int32_t)(uint32_t)(u >> 32);
+    int64_t r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(nq), "r"(p.m_lo_s), "l"((int64_t)h));
+    uint32_t r_hi;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r_hi) : "r"((uint32_t)nq), "r"(p.m_hi_adj), "r"((uint32_t)((uint64_t)r >> 32)));
+    const uint64_t rr = ((uint64_t)r_hi << 32) | (uint32_t)r;
+    return rr >= p.m ? rr - p.m : rr;
+}
+
 __device__ __forceinline__ uint64_t mod_any(uint64_t h, const Part2Dev &p) {
     if (p.recip_fits32) return mod_big(h, p.m, (uint32_t)p.recip);
     const uint64_t q = __umul64hi(h, p.recip);
@@ -70,96 +101,8 @@ __device__ __forceinline__ uint64_t mod_any(uint64_t h, const Part2Dev &p) {
     return r >= p.m ? r - p.m : r;
 }
 
-template <int KG, int NG>
-__global__ void __launch_bounds__(256, 4) bloom_part2_fixed16(const uint4 *__restrict__ keys, uint64_t n, Part2Dev p) {
-    __shared__ uint32_t hist[2][kMaxWindows2];
-    __shared__ uint32_t tbase[2][kMaxWindows2];  // absolute entry number (w*cap + pos) of the tile's first entry
-    __shared__ uint32_t cur[kMaxWindows2], lim[kMaxWindows2];  // window-relative: next free / end of quota
-    const uint32_t tid = threadIdx.x;
-    const uint32_t W = p.n_windows;
-    const uint32_t mask = (1u << p.window_log2) - 1u;
-    for (uint32_t w = tid; w < W; w += blockDim.x) {
-        hist[0][w] = 0;
-        hist[1][w] = 0;
-        cur[w] = 0;
-        lim[w] = 0;
-    }
-    __syncthreads();
-    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
-    uint32_t pp = 0;
-    uint64_t tile = blockIdx.x;
-    uint4 nextk = make_uint4(0, 0, 0, 0);
-    if (tile < tiles && tile * blockDim.x + tid < n) nextk = __ldcs(keys + tile * blockDim.x + tid);
-    for (; tile < tiles; tile += gridDim.x) {
-        const uint64_t i = tile * blockDim.x + tid;
-        const bool live = i < n;
-        const uint4 kw = nextk;
-        {
-            const uint64_t ni = (tile + gridDim.x) * blockDim.x + tid;
-            if (ni < n) nextk = __ldcs(keys + ni);
-        }
-        uint32_t loc[NG * KG];
-        uint32_t wr[NG * KG];  // window << 16 | rank within the tile
-        if (live) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                uint64_t h[KG];
-                fnv_group_16<KG>(kw, g * KG, h);
-#pragma unroll
-                for (int j = 0; j < KG; ++j) {
-                    if ((uint32_t)(g * KG + j) < p.k) {
-                        const uint64_t idx = mod_any(h[j], p);
-                        const uint32_t w = (uint32_t)(idx >> p.window_log2);
-                        loc[g * KG + j] = (uint32_t)idx & mask;
-                        wr[g * KG + j] = (w << 16) | atomicAdd(&hist[pp][w], 1u);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (uint32_t w = tid; w < W; w += blockDim.x) {
-            const uint32_t need = hist[pp][w];
-            uint32_t c = cur[w];
-            if (need) {
-                uint32_t e = lim[w];
-                if (c + need > e) {
-                    // hand back what is left of the old quota as sentinels, then reserve a new one
-                    const uint32_t stop = e < p.cap ? e : p.cap;
-                    for (uint32_t q = c; q < stop; ++q) p.stage[w * p.cap + q] = kSentinel;
-                    const uint32_t take = need > p.quota ? need : p.quota;
-                    c = atomicAdd(p.cursors + w, take);
-                    lim[w] = c + take;
-                }
-                cur[w] = c + need;
-            }
-            tbase[pp][w] = c;
-            hist[pp ^ 1][w] = 0;
-        }
-        __syncthreads();
-        if (live) {
-#pragma unroll
-            for (int s = 0; s < NG * KG; ++s) {
-                if ((uint32_t)s < p.k) {
-                    const uint32_t w = wr[s] >> 16;
-                    const uint32_t pos = tbase[pp][w] + (wr[s] & 0xFFFFu);
-                    if (pos < p.cap) {
-                        __stcs(p.stage + (w * p.cap + pos), loc[s]);
-                    } else {  // window list full (skewed keys): straight to the bitmap
-                        part_overflow(p, ((uint64_t)w << p.window_log2) | loc[s]);
-                    }
-                }
-            }
-        }
-        pp ^= 1;
-    }
-    __syncthreads();
-    for (uint32_t w = tid; w < W; w += blockDim.x) {
-        const uint32_t e = lim[w] < p.cap ? lim[w] : p.cap;
-        for (uint32_t q = cur[w]; q < e; ++q) p.stage[w * p.cap + q] = kSentinel;
-    }
-}
-
-// ---- third generation: same bookkeeping as bloom_part2_fixed16, but the tile's indices are first sorted by
+// ---- third generation (round 1; kept as the cross-check of bloom_part4 and for the P2P direct-store variant):
+// quota cursors as described above, and the tile's indices are first sorted by
 // window in shared memory and then copied out by consecutive threads, so a warp's 32 stores fall into one to
 // three contiguous runs instead of ~20 scattered 4-byte writes.  The round-1 profiles showed pass 1 pinned
 // at ~45 G L2 write requests/s whatever the window count (time grew with the number of windows because the
@@ -319,6 +262,10 @@ static void launch_part3(bool big_tile, int grid, cudaStream_t stream, const uin
     }
     bloom_part3_fixed16<KG, NG, P2P, 256><<<grid, 256, 0, stream>>>(keys, n, pd, dst);
 }
+
+// fourth generation of pass 1 (pb_bloom_part4.cu): any key layout, K = 1..16 hashes
+constexpr uint32_t kMaxPartK = 16;  // partitioned insert is instantiated for 1..16 hashes (more take the direct path)
+cudaError_t launch_part4(uint32_t k, bool big_tile, int grid, cudaStream_t stream, const DevKeys &dk, const Part2Dev &pd);
 
 // pass 2: one window at a time (launch order); its bitmap slice stays L2 resident while its list streams by
 static __global__ void __launch_bounds__(256) bloom_apply2(Part2Dev p, uint32_t ctas_per_window) {

@@ -73,7 +73,7 @@ struct pb_ctx {
                                          // windows being updated stay L2 resident; 4 x 32 MiB at once thrashed: r1 sweep)
     int64_t bloom_part_tile = 0;         // keys per pass-1 tile: 0 auto (512 beyond 112 windows), 256, 512
     int64_t bloom_overlap = 1;           // run pass 2 of chunk i on aux_stream while pass 1 of chunk i+1 runs
-    int64_t bloom_part_version = 3;      // 1: first partition kernels, 2: quota cursors + prefetch, 3: + smem-sorted coalesced copy-out
+    int64_t bloom_part_version = 4;      // pass 1 of the partitioned insert: 4 = bloom_part4 (any key layout), 3 = round-1 kernel (cross-check)
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics

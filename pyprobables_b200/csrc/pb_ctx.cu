@@ -560,6 +560,19 @@ void pbt_cuckoo_info(uint64_t h, uint32_t fp_bits, uint64_t capacity, uint32_t *
     *i1 = fastmod(*fp, f);
     *i2 = fastmod(fnv_of_decimal(*fp), f);
 }
+// host twin of mod_fast33 (pb_bloom_part.cuh): the same steps in portable C, for m >= 2^33
+uint64_t pbt_mod_fast33(uint64_t h, uint64_t m) {
+    const uint32_t r32 = (uint32_t)make_fastmod(m).recip;
+    const int32_t m_lo_s = (int32_t)(uint32_t)m;
+    const uint32_t m_hi_adj = (uint32_t)(m >> 32) + (uint32_t)((m >> 31) & 1u);
+    const uint32_t t_hi = (uint32_t)(((uint64_t)(uint32_t)h * r32) >> 32);
+    const uint64_t u = (uint64_t)(uint32_t)(h >> 32) * r32 + t_hi;
+    const int32_t nq = (int32_t)(0u - (uint32_t)(u >> 32));
+    const uint64_t r = h + (uint64_t)((int64_t)nq * (int64_t)m_lo_s);
+    const uint32_t r_hi = (uint32_t)(r >> 32) + (uint32_t)nq * m_hi_adj;
+    const uint64_t rr = ((uint64_t)r_hi << 32) | (uint32_t)r;
+    return rr >= m ? rr - m : rr;
+}
 uint64_t pbt_sm64(uint64_t x) { return sm64(x); }
 int pbt_pick_group(uint32_t k) { return pick_group(k); }
 

@@ -138,12 +138,12 @@ struct KeyRef {
     uint32_t len;  // symbols
 };
 
-// Stage keys [first, first+count) of dk (count <= blockDim.x) and return this thread's key
-// (thread t owns key first+t; threads beyond count get len 0 and must not use the key).
-// All threads of the CTA must call this; `parity` is the CTA-uniform mbarrier phase, flipped on use.
+// Stage keys [first, first+count) of dk (count <= blockDim.x) into `buf` (cap_bytes, 128-byte aligned shared
+// memory) and return this thread's key (thread t owns key first+t; threads beyond count get len 0 and must not use
+// the key).  All threads of the CTA must call this; `parity` is the CTA-uniform mbarrier phase, flipped on use.
 template <int SYMW>
-__device__ __forceinline__ KeyRef stage_tile(const DevKeys &dk, uint64_t first, uint32_t count, TileSmem &sm,
-                                             uint32_t &parity) {
+__device__ __forceinline__ KeyRef stage_tile_buf(const DevKeys &dk, uint64_t first, uint32_t count, uint8_t *buf,
+                                                 uint32_t cap_bytes, uint64_t *bar, uint32_t &parity) {
     const uint32_t t = threadIdx.x;
     uint64_t sym_beg, sym_end, my_beg = 0, my_end = 0;
     if (dk.offsets) {
@@ -168,32 +168,38 @@ __device__ __forceinline__ KeyRef stage_tile(const DevKeys &dk, uint64_t first, 
     const uint64_t span = (uint64_t)(g_end - a_beg);
     KeyRef r;
     r.len = (uint32_t)(my_end - my_beg);
-    if (span > kStageBytes || g_end <= g_beg) {
+    if (span > cap_bytes || g_end <= g_beg) {
         // oversize (or empty) tile: read straight from global memory
         r.p = dk.data + my_beg * SYMW;
         return r;
     }
-    __syncthreads();  // every thread is done reading the previous tile out of sm.buf
+    __syncthreads();  // every thread is done reading the previous tile out of buf
     const uint32_t bulk = a_end > a_beg ? (uint32_t)(a_end - a_beg) : 0u;
     if (bulk) {
         if (t == 0) {
             fence_proxy_async_smem();  // order prior generic-proxy reads of buf before the async-proxy write
-            mbar_expect_tx(&sm.bar, bulk);
-            tma_bulk_g2s(sm.buf, a_beg, bulk, &sm.bar);
+            mbar_expect_tx(bar, bulk);
+            tma_bulk_g2s(buf, a_beg, bulk, bar);
         }
     }
     // the < 16 tail bytes (and the whole span when it never reaches a 16-byte boundary)
     const uint8_t *tail_src = bulk ? a_end : a_beg;
     const uint32_t tail_off = bulk;
     const uint32_t tail_n = (uint32_t)(g_end - tail_src);
-    for (uint32_t i = t; i < tail_n; i += blockDim.x) sm.buf[tail_off + i] = tail_src[i];
+    for (uint32_t i = t; i < tail_n; i += blockDim.x) buf[tail_off + i] = tail_src[i];
     if (bulk) {
-        mbar_wait(&sm.bar, parity);
+        mbar_wait(bar, parity);
         parity ^= 1u;
     }
     __syncthreads();
-    r.p = sm.buf + (uint32_t)(g_beg - a_beg) + (uint32_t)((my_beg - sym_beg) * SYMW);
+    r.p = buf + (uint32_t)(g_beg - a_beg) + (uint32_t)((my_beg - sym_beg) * SYMW);
     return r;
+}
+
+template <int SYMW>
+__device__ __forceinline__ KeyRef stage_tile(const DevKeys &dk, uint64_t first, uint32_t count, TileSmem &sm,
+                                             uint32_t &parity) {
+    return stage_tile_buf<SYMW>(dk, first, count, sm.buf, kStageBytes, &sm.bar, parity);
 }
 
 // True when the fast register path applies.

@@ -251,13 +251,11 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
         pd.stage = p->direct ? nullptr : p->lstage[h];
         pd.cursors = p->scur[h];
         pd.words = nullptr;
-        pd.m = num_bits;
-        pd.recip = make_fastmod(num_bits).recip;
+        part_set_modulus(pd, num_bits);
         pd.cap = p->cap;
         pd.window_log2 = window_log2;
         pd.n_windows = W;
         pd.k = k;
-        pd.recip_fits32 = num_bits > (1ull << 32) ? 1u : 0u;
         const int grid = grid_for(ctx, keys->n, 256, 4);
         const bool big_tile = grid >= 2 && (ctx->bloom_part_tile == 512 || (ctx->bloom_part_tile != 256 && W > 112));
         {
@@ -275,28 +273,35 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
         dst.wps = p->wps;
         dst.src_rank = p->rank;
         const uint4 *k4 = (const uint4 *)keys->data;
-        const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
         launch_begin(ctx);
-        switch (ng * 100 + kg) {
-#define PB_P3(KG, NG)                                                                                          \
-    do {                                                                                                       \
-        if (p->direct) launch_part3<KG, NG, true>(big_tile, grid, ctx->stream, k4, keys->n, pd, dst);   \
-        else launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, keys->n, pd, dst);            \
-    } while (0)
-            case 101: PB_P3(1, 1); break;
-            case 102: PB_P3(2, 1); break;
-            case 103: PB_P3(3, 1); break;
-            case 104: PB_P3(4, 1); break;
-            case 105: PB_P3(5, 1); break;
-            case 106: PB_P3(6, 1); break;
-            case 107: PB_P3(7, 1); break;
-            case 108: PB_P3(8, 1); break;
-            case 205: PB_P3(5, 2); break;
-            case 206: PB_P3(6, 2); break;
-            case 207: PB_P3(7, 2); break;
-            case 208: PB_P3(8, 2); break;
+        if (!p->direct && ctx->bloom_part_version != 3) {
+            // DMA variant: the staging is local and contiguous, exactly the single-GPU layout
+            DevKeys dk;
+            dk.data = (const uint8_t *)keys->data;
+            dk.offsets = nullptr;
+            dk.n = keys->n;
+            dk.stride = 16;
+            dk.sym_width = 1;
+            dk.base_symbol = 0;
+            dk.total_bytes = keys->n * 16;
+            cudaError_t e = launch_part4(k, big_tile, grid, ctx->stream, dk, pd);
+            if (e != cudaSuccess) {
+                set_error("launch of bloom_part4 (k=%u) failed: %s", k, cudaGetErrorString(e));
+                return PB_ERR_CUDA;
+            }
+        } else {
+            const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
+            switch (ng * 100 + kg) {
+#define PB_P3(KG, NG)                                                                                        \
+    case NG * 100 + KG:                                                                                      \
+        if (p->direct) launch_part3<KG, NG, true>(big_tile, grid, ctx->stream, k4, keys->n, pd, dst);        \
+        else launch_part3<KG, NG, false>(big_tile, grid, ctx->stream, k4, keys->n, pd, dst);                 \
+        break;
+                PB_P3(1, 1) PB_P3(2, 1) PB_P3(3, 1) PB_P3(4, 1) PB_P3(5, 1) PB_P3(6, 1) PB_P3(7, 1) PB_P3(8, 1)
+                PB_P3(5, 2) PB_P3(6, 2) PB_P3(7, 2) PB_P3(8, 2)
 #undef PB_P3
-            default: set_error("internal: no partition kernel for k=%u", k); return PB_ERR_UNSUPPORTED;
+                default: set_error("internal: no partition kernel for k=%u", k); return PB_ERR_UNSUPPORTED;
+            }
         }
         PB_TRY(check_launch(ctx, "bloom_part"));
     }

@@ -91,6 +91,20 @@ def test_fastmod_exact(native, golden):
                 assert [L.pbt_fastmod(h, kat["m"]) for h in hashes] == bits
 
 
+def test_mod_fast33_exact(native):
+    """host twin of the partition kernels' modulo for m >= 2^33 (signed mad.wide form) against Python's %"""
+    L = native.lib()
+    rng = np.random.default_rng(33)
+    moduli = [2**33, 2**33 + 1, 9585058424, 143775874672, 2**34 - 1, 2**40 + 12345, 2**63 - 1, 2**63, 2**63 + 1, 2**64 - 1]
+    moduli += [int(x) for x in rng.integers(2**33, 2**64 - 1, size=50, dtype=np.uint64)]
+    for m in moduli:
+        hs = [0, 1, m - 1, m, m + 1, 2 * m - 1, 2 * m, 2**64 - 1, 2**64 - 2, 2**63, (2**64 // m) * m - 1, (2**64 // m) * m]
+        hs += [int(x) for x in rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64)]
+        for h in hs:
+            h %= 2**64
+            assert L.pbt_mod_fast33(h, m) == h % m, (h, m)
+
+
 def test_cuckoo_index_hook(native, golden, orc):
     L = native.lib()
     keys = orc.uniform_keys(0, 8)
