@@ -481,8 +481,8 @@ def main() -> None:
     ap.add_argument("--keys", type=int, default=10**9, help="keys per GPU per step")
     ap.add_argument("--e2e-keys", type=int, default=1 << 27)
     ap.add_argument("--ref-keys", type=int, default=100_000, help="keys per step of the pure-Python reference arm")
-    ap.add_argument("--chunk-keys", type=int, default=1 << 26)
-    ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "p2p_direct", "fused", "route", "gather"])
+    ap.add_argument("--chunk-keys", type=int, default=1 << 27)
+    ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "route", "gather"])
     ap.add_argument("--insert-mode", type=int, default=0, help="bloom_insert_mode: 0 auto, 1 direct RED, 2 partitioned")
     ap.add_argument("--window-log2", type=int, default=0, help="bloom_window_log2_bits override")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable), e.g. bloom_part_tile=256")

@@ -43,6 +43,7 @@ typedef struct pb_ctx pb_ctx;
 typedef struct pb_bloom pb_bloom;
 typedef struct pb_cms pb_cms;
 typedef struct pb_cuckoo pb_cuckoo;
+typedef struct pb_cbloom pb_cbloom;
 
 /* A batch of keys (KeyT = str | bytes, hashes.py:10).
  *   data      packed symbols of all keys, back to back.
@@ -78,6 +79,7 @@ int pb_ctx_launch_count(pb_ctx *ctx, uint64_t *out);
 int pb_ctx_kernel_times(pb_ctx *ctx, char *buf, size_t cap);
 /* tuning knobs: "bloom_insert_mode" (0 = auto, 1 = direct RED.OR, 2 = partition + L2-window apply),
  * "bloom_window_log2_bits", "stage_bytes" (staging budget for partitioned insert),
+ * "bloom_min_chunks" (chunks a large batch is split into so pass 2 overlaps the next pass 1), "p2p_timeout_ms",
  * "h2d_chunk_keys" (host-buffer pipeline chunk), "cms_aggregate" (warp-combine equal keys, default 1),
  * "cuckoo_serial" (1 = one-thread in-order cuckoo insert that reproduces the reference's append order),
  * "kernel_timing" (1 = bracket hot kernels with events, see pb_ctx_kernel_times). */
@@ -99,10 +101,16 @@ int pb_flush_l2(pb_ctx *ctx);
 /* default_fnv_1a(key, depth) for every key: out[i*depth + s] = fnv_1a(key_i, seed = s). */
 int pb_hash_keys(pb_ctx *ctx, const pb_keys *keys, uint32_t depth, uint64_t *out, int out_on_device);
 
+/* fnv_1a(key, seed) (bits = 64, hashes.py:86-103) / fnv_1a_32(key, seed) (bits = 32, :106-122) with ANY seed: one
+ * hash per key from the explicit start value (offset basis + 31*seed, reduced by the caller): out[i]. */
+int pb_hash_keys_from(pb_ctx *ctx, const pb_keys *keys, uint64_t start_value, int bits, uint64_t *out, int out_on_device);
+
 /* synthetic inputs of SURVEY.md 8(d) generated on the device (bench/test utility, not reference
  * code): uniform key i = LE64(sm64(seed+2i)) || LE64(sm64(seed+2i+1)); rank key = LE64(r)||LE64(sm64(r)) */
 int pb_gen_uniform_keys(pb_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, void *out_dev);
 int pb_gen_rank_keys(pb_ctx *ctx, const uint64_t *ranks_dev, uint64_t n, void *out_dev);
+/* Zipf(a) ranks (config 3's stream) drawn on the device: rank i depends only on (seed, first + i) */
+int pb_gen_zipf_ranks(pb_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, double a, uint64_t *out_ranks_dev);
 
 /* ---------------------------------------------------------------- Bloom (blooms/bloom.py) */
 /* state = ceil(num_bits/8) bytes, bit b lives in byte b/8 at mask 1<<(b%8) (bloom.py:247-249).
@@ -136,41 +144,73 @@ int pb_bloom_create_shard(pb_ctx *ctx, uint64_t num_bits, uint32_t k, uint64_t l
  * All buffers are device pointers (they feed an NCCL all-to-all). */
 int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint64_t shard_bits,
                         uint32_t n_shards, uint64_t *out_idx_dev, uint64_t slot_cap, uint64_t *counts_dev);
-/* Fused route + partition (the fast multi-GPU insert): hash -> % num_bits -> bin by GLOBAL window of
- * 2^window_log2 bits (window g belongs to rank g / windows_per_rank) as window-local u32 into
- * stage_dev[n_windows][cap], counts in cursors_dev[n_windows] (they may exceed cap; entries past cap went to
- * ovf_list_dev as global u64 indices, *ovf_count_dev counts them).  One equal-split all-to-all of stage_dev
- * and cursors_dev delivers every rank its windows; pb_bloom_apply_window_lists ORs them into the shard.
- * Stream-ordered, no host synchronization.  pb_bloom_partition_slack: entries a list needs beyond its
- * expected share. */
-int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
-                            uint32_t n_windows, uint32_t cap, uint32_t *stage_dev, uint32_t *cursors_dev,
-                            uint64_t *ovf_list_dev, uint64_t ovf_cap, uint64_t *ovf_count_dev);
-int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint32_t n_windows, uint64_t *out_entries);
-int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const uint32_t *cursors_dev, uint32_t n_sources,
-                                uint32_t windows_per_source, uint32_t windows, uint32_t cap, uint32_t window_log2);
-/* The same insert as ONE fused compute + exchange kernel over NVLink peer memory (no NCCL on the data path):
- * every rank owns a mailbox (window lists per source rank, double buffered) that all peers map through CUDA
- * IPC; pb_p2p_partition_send hashes a chunk of keys and stores each bit index straight into the list of its
- * window inside the OWNER's mailbox, then publishes the list lengths and raises per-source flags;
- * pb_p2p_apply on the owner waits for all sources' flags, ORs the lists into its shard and raises the flags that
- * let the sources reuse that half.  Both calls are stream-ordered and never synchronise the host; every rank
- * must call them the same number of times.  handles: world x 64 bytes from pb_p2p_export of every rank. */
+/* The fast multi-GPU insert: partition + exchange over NVLink peer memory + apply (no NCCL on the data path).
+ * Every rank owns a mailbox (window sublists per source rank, three rotating buffers) that all peers map through
+ * CUDA IPC.  pb_p2p_partition_send hashes a chunk of keys and bins the bit indices by GLOBAL window of
+ * 2^window_log2 bits (window g belongs to rank g / windows_per_rank) as window-local u32 into a local staging laid
+ * out [window][n_sub][sub_cap] -- one private sublist per CTA of the launch, so the kernel needs no global atomics --
+ * then the copy engines push every destination's block into its mailbox and a publish kernel raises per-source
+ * flags; pb_p2p_apply on the owner waits for all sources' flags, ORs the lists into its shard (window L2 resident)
+ * and raises the flags that let the sources reuse the buffer.  Both calls are stream-ordered and never synchronise
+ * the host; every rank must call them the same number of times.  Indices that do not fit their sublist go to
+ * ovf_list_dev as global u64 indices (*ovf_count_dev counts them) for the caller to route exactly.
+ * Flag waits are bounded by the "p2p_timeout_ms" option; pb_p2p_check reports who gave up.
+ * pb_bloom_partition_layout: the (n_sub, sub_cap) a mailbox needs for chunks of up to n_keys keys per rank. */
 typedef struct pb_p2p pb_p2p;
-int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t windows_per_rank, uint32_t cap, pb_p2p **out);
-/* exchange variant, before the first chunk: 0 (default) = pass 1 fills a local staging and the copy engines
- * push each destination's block over NVLink (SMs stay with the compute passes); 1 = pass 1 stores every entry
- * straight into the owner's mailbox (SM stores over NVLink, no staging) */
-int pb_p2p_set_direct(pb_p2p *p, int direct_stores);
+int pb_bloom_partition_layout(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint64_t num_bits, uint32_t window_log2,
+                              uint32_t n_windows, uint32_t *n_sub, uint32_t *sub_cap);
+int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t windows_per_rank, uint32_t n_sub,
+                  uint32_t sub_cap, pb_p2p **out);
 int pb_p2p_export(pb_p2p *p, uint8_t *handle_out /* 64 bytes */);
 int pb_p2p_connect(pb_p2p *p, const uint8_t *handles /* world * 64 bytes */);
+/* ranks living in one process (several shards driven by one host thread): connect by pointer, peers[r] = rank r */
+int pb_p2p_connect_local(pb_p2p *p, pb_p2p *const *peers);
 int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
                           uint64_t *ovf_list_dev, uint64_t ovf_cap, uint64_t *ovf_count_dev);
 int pb_p2p_apply(pb_p2p *p, pb_bloom *shard, uint32_t active_windows, uint32_t window_log2);
+/* *aborted_by = 0 when healthy, else 1 + the rank whose flag wait timed out first (synchronous device read) */
+int pb_p2p_check(pb_p2p *p, int *aborted_by);
 int pb_p2p_destroy(pb_p2p *p);
+/* multi-GPU query: global bit indices of device keys in key order, out_idx_dev[i*k + s] = h_s(key_i) % num_bits
+ * (they travel to the owners of their bits; pb_bloom_test_bit_indices answers; pb_bloom_and_rows folds the k
+ * answers of each key at the source) */
+int pb_bloom_index_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint64_t *out_idx_dev);
+int pb_bloom_and_rows(pb_ctx *ctx, const uint8_t *bits_dev, uint64_t n, uint32_t k, uint8_t *out_dev);
 /* apply global bit indices that fall into this shard's [lo, hi) (others are an error count) */
 int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n);
 int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, uint8_t *out_dev);
+
+/* ---------------------------------------------------------------- Counting Bloom (blooms/countingbloom.py) */
+/* state = uint32[num_counters] (array('I'), bloom_length == number_bits, countingbloom.py:77-78);
+ * counter of hash i = h_i % num_counters (:143). */
+int pb_cbloom_create(pb_ctx *ctx, uint64_t num_counters, uint32_t k, pb_cbloom **out);
+int pb_cbloom_destroy(pb_cbloom *b);
+int pb_cbloom_clear(pb_cbloom *b);
+int pb_cbloom_upload(pb_cbloom *b, const uint32_t *counts, uint64_t n);
+int pb_cbloom_download(pb_cbloom *b, uint32_t *counts, uint64_t n);
+int pb_cbloom_device_ptr(pb_cbloom *b, void **out_dev, uint64_t *out_count);
+/* CountingBloomFilter.add for every key (:125-153): each (key, hash) pair adds num_els to its counter -- colliding
+ * hashes of one key increment twice, as in the reference -- saturating at UINT32_MAX (:147-149). */
+int pb_cbloom_add_keys(pb_cbloom *b, const pb_keys *keys, uint64_t num_els);
+int pb_cbloom_add_hashes(pb_cbloom *b, const uint64_t *hashes, uint64_t n, int on_device, uint64_t num_els);
+/* CountingBloomFilter.check (:155-174): out[i] = smallest of the key's counters */
+int pb_cbloom_check_keys(pb_cbloom *b, const pb_keys *keys, uint32_t *out, int out_on_device);
+int pb_cbloom_check_hashes(pb_cbloom *b, const uint64_t *hashes, uint64_t n, int on_device, uint32_t *out,
+                           int out_on_device);
+/* CountingBloomFilter.remove for every key IN ORDER (:176-208): a key removes min(num_els, its smallest counter)
+ * from each of its counters, skips saturated counters and does nothing when its smallest counter is 0 or
+ * UINT32_MAX.  *removed_total = sum of what the keys removed (what elements_added shrinks by, :207). */
+int pb_cbloom_remove_keys(pb_cbloom *b, const pb_keys *keys, uint64_t num_els, uint64_t *removed_total);
+int pb_cbloom_remove_hashes(pb_cbloom *b, const uint64_t *hashes, uint64_t n, int on_device, uint64_t num_els,
+                            uint64_t *removed_total);
+/* out4[0] = non-zero counters (_cnt_number_bits_set, :328-330), [1] = sum of all counters, [2] = largest counter,
+ * [3] = first index holding it (__str__, :100-123) */
+int pb_cbloom_stats(pb_cbloom *b, uint64_t *out4);
+/* union (op 0, :300-326) / intersection (op 1, :210-243): dst[i] = a[i] + b[i] (saturating), for the intersection
+ * only where both are non-zero */
+int pb_cbloom_combine(pb_cbloom *dst, pb_cbloom *a, pb_cbloom *b, int op);
+/* jaccard_index (:245-272): counts[0] = counters non-zero in a or b, counts[1] = non-zero in both */
+int pb_cbloom_pair_counts(pb_cbloom *a, pb_cbloom *b, uint64_t *counts);
 
 /* ---------------------------------------------------------------- Count-Min (countminsketch.py) */
 /* state = int32[depth][width] row-major; bin of row i = (h_i % width) + i*width (:275). */
@@ -196,6 +236,10 @@ int pb_cms_check_hashes(pb_cms *c, const uint64_t *hashes, uint64_t n, int on_de
                         int64_t elements_added, int64_t *out, int out_on_device);
 /* CountMinSketch.join (:380-391) against a second table already on this device (multi-GPU merge) */
 int pb_cms_join_buffer(pb_cms *c, const int32_t *other_dev, uint64_t count);
+/* multi-GPU merge as ONE all-reduce: the table widened to int64, and a table loaded from int64 sums with the
+ * reference's saturation (for non-negative tables a chain of saturating joins equals min(sum, INT32_MAX)) */
+int pb_cms_widen(pb_cms *c, int64_t *out_dev, uint64_t count);
+int pb_cms_load_sums(pb_cms *c, const int64_t *sums_dev, uint64_t count);
 
 /* ---------------------------------------------------------------- Cuckoo (cuckoo/cuckoo.py) */
 /* state = u32[capacity][bucket_size], 0 = empty slot; fingerprint 0 (legal, utilities.py:35) is
@@ -221,6 +265,23 @@ int pb_cuckoo_check_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int ou
 /* _check_if_present (:440-446) from fingerprints (custom hash_function ran on the host) */
 int pb_cuckoo_check_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, int on_device, uint8_t *out,
                                  int out_on_device);
+/* CuckooFilter.remove (:317-330) for every key: out[i] = 1 when a stored copy of the key's fingerprint was cleared
+ * (idx_1 first, then idx_2); *n_removed is what elements_added shrinks by.  Equal keys inside one batch: exactly one
+ * of them wins. */
+int pb_cuckoo_remove_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device, uint64_t *n_removed);
+/* Pre-indexed filters -- a custom hash_function decides idx_2 = hash_function(str(fp)) % capacity (:489), which the
+ * device cannot evaluate: the caller passes idx_2 with every fingerprint (host arrays), the table keeps the idx_2
+ * of every stored fingerprint for the eviction walk (:383-385).  Inserts run in key order on one thread (the
+ * reference's append order); failed_* return the homeless (fingerprint, idx_2) pairs with PB_ERR_CUCKOO_FULL. */
+int pb_cuckoo_add_indexed(pb_cuckoo *c, const uint32_t *fps, const uint64_t *idx2, uint64_t n, uint64_t *n_added,
+                          uint64_t *n_failed, uint32_t *failed_fps, uint64_t *failed_idx2, uint64_t failed_cap);
+int pb_cuckoo_check_indexed(pb_cuckoo *c, const uint32_t *fps, const uint64_t *idx2, uint64_t n, uint8_t *out);
+int pb_cuckoo_remove_indexed(pb_cuckoo *c, const uint32_t *fps, const uint64_t *idx2, uint64_t n, uint8_t *out,
+                             uint64_t *n_removed);
+/* idx_2 per slot for an uploaded table (a file written by the reference with a custom hash), and an empty table
+ * of a new capacity (pre-indexed filters expand by re-inserting from the host, :455-481) */
+int pb_cuckoo_set_alt(pb_cuckoo *c, const uint64_t *idx2_per_slot, uint64_t count);
+int pb_cuckoo_resize(pb_cuckoo *c, uint64_t new_capacity);
 /* _generate_fingerprint_info (:492-506): per key fp, idx_1, idx_2 */
 int pb_cuckoo_fingerprint_info(pb_cuckoo *c, const pb_keys *keys, uint32_t *fp, uint64_t *idx1, uint64_t *idx2,
                                int out_on_device);

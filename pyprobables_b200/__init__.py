@@ -1,8 +1,8 @@
 """pyprobables_b200 -- B200-native batch engine for pyprobables' hash-then-scatter hot path.
 
 Same class names, constructor arguments, properties, exceptions and `hash_function` plugin seam as
-`probables` (barrust/pyprobables v0.7.0) for BloomFilter, CountMinSketch (+Mean, +MeanMin) and
-CuckooFilter, with the batch methods `add_many` / `check_many` added.  State lives in GPU memory; every
+`probables` (barrust/pyprobables v0.7.0) for BloomFilter, CountingBloomFilter, CountMinSketch (+Mean, +MeanMin)
+and CuckooFilter, with the batch methods `add_many` / `check_many` added.  State lives in GPU memory; every
 add/check runs in hand-written sm_100a CUDA kernels behind the C ABI of include/pb200.h.
 There is no CPU fallback: without libpb200.so and a CUDA device the constructors raise.
 """
@@ -10,6 +10,7 @@ There is no CPU fallback: without libpb200.so and a CUDA device the constructors
 from . import hashes
 from ._native import Context, NativeError, NoDeviceError, build, default_context, device_count
 from .bloom import BloomFilter
+from .countingbloom import CountingBloomFilter
 from .countminsketch import CountMeanMinSketch, CountMeanSketch, CountMinSketch
 from .cuckoo import CuckooFilter
 from .exceptions import (
@@ -26,6 +27,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "BloomFilter",
+    "CountingBloomFilter",
     "CountMinSketch",
     "CountMeanSketch",
     "CountMeanMinSketch",

@@ -91,8 +91,10 @@ SIGNATURES: dict[str, list] = {
     "pb_memset_dev": [_vp, _vp, _i32, C.c_size_t],
     "pb_flush_l2": [_vp],
     "pb_hash_keys": [_vp, _KP, _u32, _vp, _i32],
+    "pb_hash_keys_from": [_vp, _KP, _u64, _i32, _vp, _i32],
     "pb_gen_uniform_keys": [_vp, _u64, _u64, _u64, _vp],
     "pb_gen_rank_keys": [_vp, _vp, _u64, _vp],
+    "pb_gen_zipf_ranks": [_vp, _u64, _u64, _u64, C.c_double, _vp],
     "pb_bloom_create": [_vp, _u64, _u32, _P(_vp)],
     "pb_bloom_destroy": [_vp],
     "pb_bloom_clear": [_vp],
@@ -108,18 +110,34 @@ SIGNATURES: dict[str, list] = {
     "pb_bloom_pair_popcounts": [_vp, _vp, _P(_u64)],
     "pb_bloom_create_shard": [_vp, _u64, _u32, _u64, _u64, _P(_vp)],
     "pb_bloom_route_keys": [_vp, _KP, _u64, _u32, _u64, _u32, _vp, _u64, _vp],
-    "pb_bloom_partition_keys": [_vp, _KP, _u64, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u64, _vp],
-    "pb_bloom_partition_slack": [_vp, _u64, _u32, _u32, _P(_u64)],
-    "pb_bloom_apply_window_lists": [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32],
-    "pb_p2p_create": [_vp, _u32, _u32, _u32, _u32, _P(_vp)],
-    "pb_p2p_set_direct": [_vp, _i32],
+    "pb_bloom_partition_layout": [_vp, _u64, _u32, _u64, _u32, _u32, _P(_u32), _P(_u32)],
+    "pb_p2p_create": [_vp, _u32, _u32, _u32, _u32, _u32, _P(_vp)],
     "pb_p2p_export": [_vp, _vp],
     "pb_p2p_connect": [_vp, _vp],
+    "pb_p2p_connect_local": [_vp, _P(_vp)],
     "pb_p2p_partition_send": [_vp, _KP, _u64, _u32, _u32, _vp, _u64, _vp],
     "pb_p2p_apply": [_vp, _vp, _u32, _u32],
+    "pb_p2p_check": [_vp, _P(C.c_int)],
     "pb_p2p_destroy": [_vp],
+    "pb_bloom_index_keys": [_vp, _KP, _u64, _u32, _vp],
+    "pb_bloom_and_rows": [_vp, _vp, _u64, _u32, _vp],
     "pb_bloom_add_bit_indices": [_vp, _vp, _u64],
     "pb_bloom_test_bit_indices": [_vp, _vp, _u64, _vp],
+    "pb_cbloom_create": [_vp, _u64, _u32, _P(_vp)],
+    "pb_cbloom_destroy": [_vp],
+    "pb_cbloom_clear": [_vp],
+    "pb_cbloom_upload": [_vp, _vp, _u64],
+    "pb_cbloom_download": [_vp, _vp, _u64],
+    "pb_cbloom_device_ptr": [_vp, _P(_vp), _P(_u64)],
+    "pb_cbloom_add_keys": [_vp, _KP, _u64],
+    "pb_cbloom_add_hashes": [_vp, _vp, _u64, _i32, _u64],
+    "pb_cbloom_check_keys": [_vp, _KP, _vp, _i32],
+    "pb_cbloom_check_hashes": [_vp, _vp, _u64, _i32, _vp, _i32],
+    "pb_cbloom_remove_keys": [_vp, _KP, _u64, _P(_u64)],
+    "pb_cbloom_remove_hashes": [_vp, _vp, _u64, _i32, _u64, _P(_u64)],
+    "pb_cbloom_stats": [_vp, _P(_u64)],
+    "pb_cbloom_combine": [_vp, _vp, _vp, _i32],
+    "pb_cbloom_pair_counts": [_vp, _vp, _P(_u64)],
     "pb_cms_create": [_vp, _u32, _u32, _P(_vp)],
     "pb_cms_destroy": [_vp],
     "pb_cms_clear": [_vp],
@@ -131,6 +149,8 @@ SIGNATURES: dict[str, list] = {
     "pb_cms_add_hashes": [_vp, _vp, _u64, _i32, _vp, _i64, _P(_i64)],
     "pb_cms_check_hashes": [_vp, _vp, _u64, _i32, _i32, _i64, _vp, _i32],
     "pb_cms_join_buffer": [_vp, _vp, _u64],
+    "pb_cms_widen": [_vp, _vp, _u64],
+    "pb_cms_load_sums": [_vp, _vp, _u64],
     "pb_cuckoo_create": [_vp, _u64, _u32, _u32, _u32, _u64, _P(_vp)],
     "pb_cuckoo_destroy": [_vp],
     "pb_cuckoo_clear": [_vp],
@@ -138,6 +158,12 @@ SIGNATURES: dict[str, list] = {
     "pb_cuckoo_add_fingerprints": [_vp, _vp, _u64, _i32, _P(_u64), _P(_u64), _vp, _u64],
     "pb_cuckoo_check_keys": [_vp, _KP, _vp, _i32],
     "pb_cuckoo_check_fingerprints": [_vp, _vp, _u64, _i32, _vp, _i32],
+    "pb_cuckoo_remove_keys": [_vp, _KP, _vp, _i32, _P(_u64)],
+    "pb_cuckoo_add_indexed": [_vp, _vp, _vp, _u64, _P(_u64), _P(_u64), _vp, _vp, _u64],
+    "pb_cuckoo_check_indexed": [_vp, _vp, _vp, _u64, _vp],
+    "pb_cuckoo_remove_indexed": [_vp, _vp, _vp, _u64, _vp, _P(_u64)],
+    "pb_cuckoo_set_alt": [_vp, _vp, _u64],
+    "pb_cuckoo_resize": [_vp, _u64],
     "pb_cuckoo_fingerprint_info": [_vp, _KP, _vp, _vp, _vp, _i32],
     "pb_cuckoo_count": [_vp, _P(_u64)],
     "pb_cuckoo_download": [_vp, _vp, _u64, _P(C.c_int)],
@@ -288,6 +314,9 @@ class Context:
 
     def gen_rank_keys(self, ranks_dev: int, n: int, out_dev: int) -> None:
         call("pb_gen_rank_keys", self.handle, _vp(ranks_dev), int(n), _vp(out_dev))
+
+    def gen_zipf_ranks(self, first: int, n: int, out_dev: int, a: float = 1.1, seed: int = 0xB200) -> None:
+        call("pb_gen_zipf_ranks", self.handle, seed, int(first), int(n), float(a), _vp(out_dev))
 
     def microbench(self, words: int, n: int, op: int, reps: int = 3) -> float:
         """device milliseconds for n random atomics (op 0 RED.OR, 1 RED.ADD, 2 gather) or a copy (op 3)"""

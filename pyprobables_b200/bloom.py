@@ -352,6 +352,22 @@ class BloomFilter:
         file.write(self.bloom_numpy().tobytes())
         file.write(_FOOTER.pack(self._est_elements, self._els_added, self._fpr))
 
+    def export_c_header(self, filename) -> None:
+        """bloom.py:306-322: the hex export as a C array plus the sizing constants"""
+        from textwrap import wrap
+
+        data = ("  " + line for line in wrap(", ".join(f"0x{e:02x}" for e in bytearray.fromhex(self.export_hex())), 80))
+        bloom_type = "CountingBloomFilter" if type(self).__name__ == "CountingBloomFilter" else "standard BloomFilter"
+        with open(filename, "w", encoding="utf-8") as file:
+            print(f"/* BloomFilter Export of a {bloom_type} */", file=file)
+            print("#include <inttypes.h>", file=file)
+            print("const uint64_t estimated_elements = ", self.estimated_elements, ";", sep="", file=file)
+            print("const uint64_t elements_added = ", self.elements_added, ";", sep="", file=file)
+            print("const float false_positive_rate = ", self.false_positive_rate, ";", sep="", file=file)
+            print("const uint64_t number_bits = ", self.number_bits, ";", sep="", file=file)
+            print("const unsigned int number_hashes = ", self.number_hashes, ";", sep="", file=file)
+            print("const unsigned char bloom[] = {", *data, "};", sep="\n", file=file)
+
     def __bytes__(self) -> bytes:
         with BytesIO() as f:
             self.export(f)

@@ -221,6 +221,35 @@ __global__ void __launch_bounds__(256) popcount_kernel(const uint4 *__restrict__
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// bit indices in key order: out[i*k + s] = fnv_1a(key_i, seed s) % num_bits (multi-GPU query: the indices travel to
+// the owners of their bits, the answers come back and are ANDed per key at the source)
+template <int KG>
+__global__ void __launch_bounds__(256) bloom_index_fixed16(const uint4 *__restrict__ keys, uint64_t n, FastMod fm, uint32_t k,
+                                                           uint64_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 w = __ldcs(keys + i);
+        for (uint32_t s0 = 0; s0 < k; s0 += KG) {
+            uint64_t h[KG];
+            fnv_group_16<KG>(w, s0, h);
+#pragma unroll
+            for (int j = 0; j < KG; ++j)
+                if (s0 + j < k) out[i * k + s0 + j] = fastmod(h[j], fm);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) reduce_mod_kernel(uint64_t *__restrict__ v, uint64_t total, FastMod fm) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        v[i] = fastmod(v[i], fm);
+}
+// out[i] = AND of bits[i*k .. i*k+k) (the per-index answers of one key)
+__global__ void __launch_bounds__(256) and_rows_kernel(const uint8_t *__restrict__ bits, uint64_t n, uint32_t k, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t ok = 1u;
+        for (uint32_t s = 0; s < k; ++s) ok &= bits[i * k + s];
+        out[i] = (uint8_t)ok;
+    }
+}
+
 // ---------------------------------------------------------------- multi-GPU routing
 // hash keys, find the owning shard of every bit index, append the (global) index to that shard's slot.
 template <int KG>
@@ -321,32 +350,13 @@ static int launch_check(pb_ctx *ctx, const DevKeys &dk, const BloomDev &bd, uint
         default: st = CALL(8); break;       \
     }
 
-// Quota (list entries a CTA reserves per window at a time) for a pass-1 launch of n keys: about 1/16 of what
-// one CTA expects to write to one window, so the sentinels left in partly used quotas stay a few percent.
-static uint32_t pick_quota(uint64_t n, uint32_t k, uint32_t n_windows, int grid) {
-    const double per = (double)n * k / ((double)n_windows * (double)std::max(grid, 1));
-    uint32_t q = 32;
-    while (q < kQuota && (double)q * 16.0 < per) q <<= 1;
-    return q;
-}
-
-// 512-key tiles once a 256-key tile would give a window fewer than ~16 entries ("bloom_part_tile": 0 auto, 256, 512)
-static bool part_big_tile(const pb_ctx *ctx, uint32_t n_windows) {
-    if (ctx->bloom_part_tile == 512) return true;
-    if (ctx->bloom_part_tile == 256) return false;
-    return n_windows > 112;
-}
-
 struct PartPlan {
     bool use = false;
     uint32_t window_log2 = 0;
     uint32_t n_windows = 0;
-    uint64_t cap = 0;
     uint64_t chunk_keys = 0;
-    int version = 4;  // 3: bloom_part3_fixed16 (round 1, 16-byte keys only), 4: bloom_part4 (any key layout)
-    int halves = 1;   // 2: the staging is split in two so pass 2 of one chunk overlaps pass 1 of the next
-    uint32_t quota = kQuota;
-    int grid = 0;     // CTAs of the pass-1 launch (the staging slack depends on it)
+    int halves = 1;  // 2: the staging is split in two so pass 2 of one chunk overlaps pass 1 of the next
+    PartLayout lay{};
 };
 
 // Decide whether (and how) a batch of n keys goes through the partitioned path.
@@ -354,9 +364,7 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     PartPlan pl;
     pb_ctx *ctx = b->ctx;
     const int64_t mode = ctx->bloom_insert_mode;
-    const int version = ctx->bloom_part_version == 3 ? 3 : 4;
-    if (mode == 1 || b->k > kMaxPartK) return pl;
-    if (!fixed16 && version == 3) return pl;
+    if (mode == 1 || b->k > kMaxPartK || n == 0) return pl;
     if (b->lo_bit != 0 || b->hi_bit != b->num_bits) return pl;  // shards take routed indices instead
     const uint64_t l2 = ctx->l2_bytes ? ctx->l2_bytes : ((uint64_t)96 << 20);
     if (mode == 0) {
@@ -366,70 +374,30 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
         if ((double)n * b->k * 64.0 < 4.0 * (double)b->nbytes) return pl;
     }
     const uint32_t wl_max = 31;
-    const uint64_t max_windows = (uint64_t)kMaxWindows2;
-    uint32_t wl = (uint32_t)ctx->bloom_window_log2_bits;
-    if (wl > wl_max) wl = wl_max;
-    while (((b->num_bits + ((1ull << wl) - 1)) >> wl) > max_windows && wl < wl_max) ++wl;
+    uint32_t wl = (uint32_t)std::max<int64_t>(5, std::min<int64_t>(ctx->bloom_window_log2_bits, wl_max));
+    while (((b->num_bits + ((1ull << wl) - 1)) >> wl) > (uint64_t)kMaxWindows2 && wl < wl_max) ++wl;
     const uint64_t nw = (b->num_bits + ((1ull << wl) - 1)) >> wl;
-    if (nw > max_windows || wl < 5) return pl;
-    uint64_t stage_items = (uint64_t)ctx->stage_bytes / 4;
-    // overlap only pays when the batch needs more than one chunk anyway or is big enough to split in two
+    if (nw > (uint64_t)kMaxWindows2) return pl;
+    // overlap only pays when the batch is big enough to split; then at least "bloom_min_chunks" chunks so that the
+    // pass 2 left over after the last pass 1 is a small part of the whole
     const int halves = (ctx->bloom_overlap && n >= (1ull << 24)) ? 2 : 1;
-    stage_items /= (uint64_t)halves;
-    if (stage_items > 0xFFFFFFF0ull) stage_items = 0xFFFFFFF0ull;  // 32-bit entry numbers
-    uint64_t cap = (stage_items / nw) & ~(uint64_t)3;
-    const double per_key_per_window = (double)b->k * (double)(1ull << wl) / (double)b->num_bits;  // <= k
-    const int grid = grid_for(ctx, n, 256, 4);
-    // room every window needs beyond its expected share: statistical slack + the partly used quotas
-    const double slack = 8192.0 + (double)grid * (double)kQuota;
-    // shrink the staging to what this batch needs
-    uint64_t need = (uint64_t)((double)n * std::min(per_key_per_window, (double)b->k) * 1.03 + slack);
-    need = (need + 3) & ~(uint64_t)3;
-    if (need < cap) cap = need;
-    if ((double)cap < 2.0 * slack + 16384.0) return pl;
-    uint64_t chunk = (uint64_t)(((double)cap - slack) / 1.03 / std::min(per_key_per_window, (double)b->k));
-    chunk = std::min<uint64_t>(chunk, (0xF0000000ull - (uint64_t)grid * kQuota) / b->k);  // u32 cursors
-    if (halves == 2) chunk = std::min<uint64_t>(chunk, (n + 3) / 4);  // at least four chunks to pipeline
-    pl.halves = halves;
-    pl.quota = pick_quota(chunk, b->k, (uint32_t)nw, grid);  // <= kQuota, which the slack above allowed for
-    if (chunk < 1024) return pl;
-    pl.version = version;
-    pl.grid = grid;
+    uint64_t chunk = n;
+    if (halves == 2) chunk = std::max<uint64_t>((n + (uint64_t)ctx->bloom_min_chunks - 1) / (uint64_t)std::max<int64_t>(ctx->bloom_min_chunks, 2), 1ull << 22);
+    const uint64_t budget_entries = std::min<uint64_t>((uint64_t)ctx->stage_bytes / 4 / (uint64_t)halves, 0xFFFFFFF0ull);  // u32 entry numbers
+    PartLayout lay;
+    for (;;) {
+        lay = part_layout(ctx, chunk, b->k, b->num_bits, wl, (uint32_t)nw, fixed16);
+        if ((uint64_t)lay.sub_cap * (uint64_t)lay.grid * nw <= budget_entries) break;
+        if (chunk <= 4096) return pl;  // the staging budget cannot even hold a tiny chunk: direct path
+        chunk = chunk - chunk / 4;
+    }
     pl.use = true;
+    pl.halves = halves;
     pl.window_log2 = wl;
     pl.n_windows = (uint32_t)nw;
-    pl.cap = cap;
     pl.chunk_keys = chunk;
+    pl.lay = lay;
     return pl;
-}
-
-// pass 1 of the round-1 generation (16-byte keys only): kept selectable ("bloom_part_version" = 3) as a cross-check
-static int launch_part3_any(uint32_t k, bool big_tile, int grid, cudaStream_t stream, const uint4 *k4, uint64_t n, const Part2Dev &pd) {
-    const int kg = k <= 8 ? (int)k : (int)((k + 1) / 2), ng = k <= 8 ? 1 : 2;
-    switch (ng * 100 + kg) {
-#define PB_P3(KG, NG) \
-    case NG * 100 + KG: launch_part3<KG, NG, false>(big_tile, grid, stream, k4, n, pd, P2PDst{}); return PB_OK;
-        PB_P3(1, 1) PB_P3(2, 1) PB_P3(3, 1) PB_P3(4, 1) PB_P3(5, 1) PB_P3(6, 1) PB_P3(7, 1) PB_P3(8, 1)
-        PB_P3(5, 2) PB_P3(6, 2) PB_P3(7, 2) PB_P3(8, 2)
-#undef PB_P3
-        default: set_error("internal: no partition kernel for k=%u", k); return PB_ERR_UNSUPPORTED;
-    }
-}
-
-// Pass 1 of a key batch into stage[n_windows][cap] / cursors (zeroed here); any key layout for version 4.
-static int launch_partition(pb_ctx *ctx, int version, bool big_tile, int grid, const DevKeys &dk, const Part2Dev &pd) {
-    launch_begin(ctx);
-    if (version == 3) {
-        PB_REQUIRE(is_fixed16(dk), "the round-1 partition kernel takes 16-byte keys");
-        PB_TRY(launch_part3_any(pd.k, big_tile, grid, ctx->stream, (const uint4 *)dk.data, dk.n, pd));
-    } else {
-        cudaError_t e = launch_part4(pd.k, big_tile, grid, ctx->stream, dk, pd);
-        if (e != cudaSuccess) {
-            set_error("launch of bloom_part4 (k=%u) failed: %s", pd.k, cudaGetErrorString(e));
-            return PB_ERR_CUDA;
-        }
-    }
-    return check_launch(ctx, "bloom_part");
 }
 
 struct AddArgs {
@@ -446,32 +414,37 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
     pb_bloom *b = a->b;
     const BloomDev bd = dev_view(b);
     int st = PB_OK;
-    if (a->plan.use && (a->plan.version == 4 || is_fixed16(dk))) {
+    if (a->plan.use) {
         const PartPlan &pl = a->plan;
         const bool overlap = pl.halves == 2;
         const int half = overlap ? (int)(a->chunk_no++ & 1) : 0;
-        const size_t half_entries = (size_t)pl.n_windows * pl.cap;
+        const size_t n_lists = (size_t)pl.n_windows * (size_t)pl.lay.grid;
+        const size_t half_entries = n_lists * pl.lay.sub_cap;
         PB_TRY(scratch_reserve(ctx, ctx->part_stage, half_entries * 4 * (size_t)pl.halves));
-        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, (size_t)kMaxWindows2 * 4 * 2));
-        Part2Dev pd;
+        PB_TRY(scratch_reserve(ctx, ctx->part_cursors, n_lists * 4 * (size_t)pl.halves));
+        PartDev pd;
         pd.stage = (uint32_t *)ctx->part_stage.p + (size_t)half * half_entries;
-        pd.cursors = (unsigned int *)ctx->part_cursors.p + (size_t)half * kMaxWindows2;
+        pd.counts = (uint32_t *)ctx->part_cursors.p + (size_t)half * n_lists;
         pd.words = b->words;
         part_set_modulus(pd, b->num_bits);
-        pd.cap = (uint32_t)pl.cap;
+        pd.sub_cap = pl.lay.sub_cap;
+        pd.n_sub = (uint32_t)pl.lay.grid;
         pd.window_log2 = pl.window_log2;
         pd.n_windows = pl.n_windows;
         pd.k = b->k;
-        pd.quota = pl.quota;
         pd.ovf_list = nullptr;
         pd.ovf_count = nullptr;
         pd.ovf_cap = 0;
         // this half of the staging is free again once the pass 2 that read it last has finished
         if (overlap && ctx->apply_pending[half]) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[half], 0));
-        PB_CUDA(cudaMemsetAsync(pd.cursors, 0, (size_t)pl.n_windows * 4, ctx->stream));
-        const int grid = std::min(pl.grid, grid_for(ctx, dk.n, 256, 4));
-        const bool big_tile = part_big_tile(ctx, pl.n_windows) && grid >= 2;
-        PB_TRY(launch_partition(ctx, pl.version, big_tile, grid, dk, pd));
+        // the layout was planned for 16-byte keys or for staged keys: a batch is one or the other throughout
+        launch_begin(ctx);
+        cudaError_t e = launch_part4(pl.lay.block, ctx->stream, dk, pd);
+        if (e != cudaSuccess) {
+            set_error("launch of bloom_part4 (k=%u) failed: %s", pd.k, cudaGetErrorString(e));
+            return PB_ERR_CUDA;
+        }
+        PB_TRY(check_launch(ctx, "bloom_part"));
         const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
         cudaStream_t s2 = ctx->stream;
         if (overlap) {
@@ -479,6 +452,7 @@ static int add_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, v
             PB_CUDA(cudaEventRecord(ctx->ev_part[half], ctx->stream));
             PB_CUDA(cudaStreamWaitEvent(s2, ctx->ev_part[half], 0));
         }
+        PB_CUDA(apply_prefer_max_smem());
         launch_begin(ctx, s2);
         bloom_apply2<<<pl.n_windows * cpw, 256, 0, s2>>>(pd, cpw);
         PB_TRY(check_launch(ctx, "bloom_apply_windows", s2));
@@ -773,82 +747,56 @@ int pb_bloom_route_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uin
     return st;
 }
 
-// Multi-GPU fused route + partition: hash the keys, reduce % num_bits and bin the indices by GLOBAL window
-// (window g = idx >> window_log2 belongs to rank g / windows_per_rank) into stage_dev[n_windows][cap] as
-// window-local u32, counts in cursors_dev[n_windows].  The per-destination blocks of stage_dev are contiguous,
-// so one equal-split all-to-all delivers them.  Everything stays on the context's stream (no host sync).
-int pb_bloom_partition_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint32_t window_log2,
-                            uint32_t n_windows, uint32_t cap, uint32_t *stage_dev, uint32_t *cursors_dev, uint64_t *ovf_list_dev,
-                            uint64_t ovf_cap, uint64_t *ovf_count_dev) {
-    PB_REQUIRE(ctx && keys && stage_dev && cursors_dev && ovf_list_dev && ovf_count_dev, "NULL argument");
-    PB_REQUIRE(keys->on_device, "pb_bloom_partition_keys takes device keys");
-    PB_REQUIRE(keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 && ((uintptr_t)keys->data & 15u) == 0,
-               "partitioned routing takes fixed 16-byte keys");
-    PB_REQUIRE(k >= 1 && k <= 16, "k must be in 1..16");
-    PB_REQUIRE(window_log2 >= 5 && window_log2 <= 31, "window_log2 must be in 5..31");
-    PB_REQUIRE(n_windows >= 1 && n_windows <= (uint32_t)kMaxWindows2, "n_windows must be in 1..%d", kMaxWindows2);
-    PB_REQUIRE(((uint64_t)n_windows << window_log2) >= num_bits, "windows do not cover the filter");
-    PB_REQUIRE((cap & 3u) == 0 && (uint64_t)cap * n_windows <= 0xFFFFFFF0ull, "cap must be a multiple of 4 and cap*n_windows < 2^32");
-    PB_REQUIRE(((uintptr_t)stage_dev & 15u) == 0, "stage_dev must be 16-byte aligned");
-    PB_REQUIRE(keys->n * (uint64_t)k < 0xE0000000ull, "too many keys for one partition call");
-    DeviceGuard g(ctx->device);
-    PB_CUDA(cudaMemsetAsync(cursors_dev, 0, (size_t)n_windows * 4, ctx->stream));
+// Global bit indices of device-resident keys in key order (any key layout): out_idx_dev[i*k + s].
+int pb_bloom_index_keys(pb_ctx *ctx, const pb_keys *keys, uint64_t num_bits, uint32_t k, uint64_t *out_idx_dev) {
+    PB_REQUIRE(ctx && keys && (out_idx_dev || keys->n == 0), "NULL argument");
+    PB_REQUIRE(keys->on_device, "pb_bloom_index_keys takes device keys");
+    PB_REQUIRE(k >= 1 && num_bits >= 1, "k and num_bits must be >= 1");
+    PB_TRY(validate_keys(keys));
     if (keys->n == 0) return PB_OK;
-    Part2Dev pd;
-    pd.stage = stage_dev;
-    pd.cursors = cursors_dev;
-    pd.words = nullptr;
-    part_set_modulus(pd, num_bits);
-    pd.cap = cap;
-    pd.window_log2 = window_log2;
-    pd.n_windows = n_windows;
-    pd.k = k;
-    pd.quota = pick_quota(keys->n, k, n_windows, grid_for(ctx, keys->n, 256, 4));
-    pd.ovf_list = ovf_list_dev;
-    pd.ovf_count = (unsigned long long *)ovf_count_dev;
-    pd.ovf_cap = ovf_cap;
-    const int grid = grid_for(ctx, keys->n, 256, 4);
-    const bool big_tile = part_big_tile(ctx, n_windows) && grid >= 2;
+    DeviceGuard g(ctx->device);
+    const FastMod fm = make_fastmod(num_bits);
     DevKeys dk;
     dk.data = (const uint8_t *)keys->data;
-    dk.offsets = nullptr;
+    dk.offsets = keys->offsets;
     dk.n = keys->n;
-    dk.stride = 16;
-    dk.sym_width = 1;
+    dk.stride = keys->stride;
+    dk.sym_width = keys->sym_width;
     dk.base_symbol = 0;
-    dk.total_bytes = keys->n * 16;
-    return launch_partition(ctx, ctx->bloom_part_version == 3 ? 3 : 4, big_tile, grid, dk, pd);
+    dk.total_bytes = keys->offsets ? 0 : keys->n * (uint64_t)keys->stride * keys->sym_width;
+    if (is_fixed16(dk)) {
+        int st = PB_OK;
+        const int grid = grid_for(ctx, keys->n, 256, 8);
+        launch_begin(ctx);
+#define CALL(K) (bloom_index_fixed16<K><<<grid, 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, fm, k, out_idx_dev), check_launch(ctx, "bloom_index"))
+        PB_DISPATCH_KG(pick_group(k), CALL)
+#undef CALL
+        return st;
+    }
+    PB_TRY(hash_dev_keys(ctx, dk, k, out_idx_dev));
+    reduce_mod_kernel<<<grid_for(ctx, keys->n * k, 256, 8), 256, 0, ctx->stream>>>(out_idx_dev, keys->n * k, fm);
+    return check_launch(ctx, "bloom_index");
 }
 
-// Slack a window list needs beyond its expected share for a pb_bloom_partition_keys call of n keys
-// (partly used quotas of every CTA of the launch); callers size `cap` with it.
-int pb_bloom_partition_slack(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint32_t n_windows, uint64_t *out_entries) {
-    PB_REQUIRE(ctx && out_entries && k >= 1 && n_windows >= 1, "bad argument");
-    // every CTA of the launch can leave one partly used quota per window
-    const int grid = grid_for(ctx, n_keys, 256, 4);
-    *out_entries = (uint64_t)grid * pick_quota(n_keys, k, n_windows, grid) + 8192;
-    return PB_OK;
-}
-
-// Pass 2 on this shard for lists received from n_sources ranks: stage_dev[n_sources][windows_per_source][cap],
-// cursors_dev[n_sources][windows_per_source]; the first `windows` of every block are this shard's (a short last
-// shard has fewer than windows_per_source); window w covers the shard's bits [w << window_log2, ...).
-int pb_bloom_apply_window_lists(pb_bloom *b, const uint32_t *stage_dev, const uint32_t *cursors_dev, uint32_t n_sources,
-                                uint32_t windows_per_source, uint32_t windows, uint32_t cap, uint32_t window_log2) {
-    PB_REQUIRE(b && stage_dev && cursors_dev, "NULL argument");
-    PB_REQUIRE(n_sources >= 1 && windows >= 1 && windows <= windows_per_source, "need 1 <= windows <= windows_per_source");
-    PB_REQUIRE(window_log2 >= 5 && window_log2 <= 31 && (cap & 3u) == 0, "bad window_log2 / cap");
-    PB_REQUIRE(((uint64_t)(windows - 1) << window_log2) < (b->hi_bit - b->lo_bit), "windows reach past this shard");
-    PB_REQUIRE((b->lo_bit & ((1ull << window_log2) - 1)) == 0, "the shard must start on a window boundary");
-    pb_ctx *ctx = b->ctx;
+// out_dev[i] = AND over the k per-index answers of key i (bits_dev[i*k + s], 0/1 bytes)
+int pb_bloom_and_rows(pb_ctx *ctx, const uint8_t *bits_dev, uint64_t n, uint32_t k, uint8_t *out_dev) {
+    PB_REQUIRE(ctx && ((bits_dev && out_dev) || n == 0) && k >= 1, "bad argument");
+    if (n == 0) return PB_OK;
     DeviceGuard g(ctx->device);
-    // windows of 32 MiB and more: one window in flight (every resident CTA slot works on it) or L2 thrashes
-    const int64_t per_sm = window_log2 >= 28 ? std::max<int64_t>(ctx->bloom_apply_cpw_per_sm, 8) : ctx->bloom_apply_cpw_per_sm;
-    const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(per_sm, 32));
-    launch_begin(ctx);
-    bloom_apply_sources<<<windows * cpw, 256, 0, ctx->stream>>>(b->words, stage_dev, cursors_dev, n_sources, windows_per_source,
-                                                                cap, window_log2, cpw);
-    return check_launch(ctx, "bloom_apply_windows");
+    and_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(bits_dev, n, k, out_dev);
+    return check_launch(ctx, "bloom_and_rows");
+}
+
+// Layout of the multi-GPU exchange for chunks of up to n_keys keys per rank (pb_p2p_create takes the two numbers):
+// sublists per window = CTAs of the pass-1 launch, entries per sublist = a CTA's expected share + 7 sigma.
+int pb_bloom_partition_layout(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint64_t num_bits, uint32_t window_log2,
+                              uint32_t n_windows, uint32_t *n_sub, uint32_t *sub_cap) {
+    PB_REQUIRE(ctx && n_sub && sub_cap && n_keys >= 1 && k >= 1 && k <= kMaxPartK, "bad argument (k must be 1..%u)", kMaxPartK);
+    PB_REQUIRE(window_log2 >= 5 && window_log2 <= 31 && n_windows >= 1 && n_windows <= (uint32_t)kMaxWindows2, "bad window geometry");
+    const PartLayout L = part_layout(ctx, n_keys, k, num_bits, window_log2, n_windows, true);
+    *n_sub = (uint32_t)L.grid;
+    *sub_cap = L.sub_cap;
+    return PB_OK;
 }
 
 int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n) {

@@ -12,8 +12,9 @@ namespace pb {
 //     run start}, so the scatter into shared memory is one LDS.64 + one STS.64 per index and the copy-out is one
 //     LDS.64, one add and one STG per index -- no window id is stored or looked up again, no bounds test per
 //     index (a tile whose lists would overflow takes a slow path that is chosen once per tile);
-//   * every warp scans its own slice of the histogram (the sum of the preceding slices is a strided read + warp
-//     reduce), so there is no single-warp serial section however many windows there are;
+//   * phase B gives every window its own thread; a warp gets the offset of its 32 windows from a strided read of
+//     the histogram in front of them + one warp reduction, so there is neither a single-warp serial section nor a
+//     second barrier, however many windows there are;
 //   * the keys come through a KeySource: 16-byte keys in registers (LDG.128, prefetched one tile ahead) or any
 //     other shape staged per tile into shared memory with one TMA bulk copy (stage_tile), which gives
 //     variable-length / str batches the partitioned path too.
@@ -50,7 +51,7 @@ constexpr uint32_t kRankStep = 8;                 // the histogram counts in uni
 // The histogram word of window w starts at w << 16, so the atomic's return value already is
 // (window << 16 | rank * 8): nothing to pack.
 template <bool FAST33>
-__device__ __forceinline__ void part4_bin(uint64_t h, const Part2Dev &p, uint32_t mask, uint32_t *hist, uint32_t &loc, uint32_t &wr) {
+__device__ __forceinline__ void part4_bin(uint64_t h, const PartDev &p, uint32_t mask, uint32_t *hist, uint32_t &loc, uint32_t &wr) {
     const uint64_t idx = FAST33 ? mod_fast33(h, p) : mod_any(h, p);
     const uint32_t w = __funnelshift_r((uint32_t)idx, (uint32_t)(idx >> 32), p.window_log2);  // window_log2 <= 31
     loc = (uint32_t)idx & mask;
@@ -58,13 +59,13 @@ __device__ __forceinline__ void part4_bin(uint64_t h, const Part2Dev &p, uint32_
 }
 
 template <int K, int BS, class KS>
-__global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Part2Dev p) {
+__global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, PartDev p) {
     constexpr int NG = PartGroups<K>::NG, KG = PartGroups<K>::KG;
-    constexpr int NW = BS / 32;
+    constexpr uint32_t NW = BS / 32;
     static_assert(BS * K * kRankStep <= 65536, "rank * 8 must fit the low 16 bits of a histogram word");
     __shared__ uint32_t hist[2][kMaxWindows2];  // window << 16 | entries of the tile so far * 8
     __shared__ Part4Tab tab[kMaxWindows2];
-    __shared__ uint32_t cur[kMaxWindows2], lim[kMaxWindows2];
+    __shared__ uint32_t cur[kMaxWindows2];  // entries written so far to this CTA's sublist of each window
     __shared__ uint2 sorted[BS * K];  // {window-local bit index, gdelta}; slow path: {index, window}
     __shared__ uint32_t tile_flags[2];  // [0]: a list of this tile overflows -> slow path; [1]: entries in the tile
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // staged key bytes (KeySrcStaged only)
@@ -75,7 +76,6 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
         hist[0][w] = w << 16;
         hist[1][w] = w << 16;
         cur[w] = 0;
-        lim[w] = 0;
     }
     if (tid == 0) tile_flags[0] = 0;
     uint64_t *bar = reinterpret_cast<uint64_t *>(dyn_smem + kPart4StageBytes);
@@ -85,10 +85,6 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
     }
     __syncthreads();
     const uint64_t tiles = (n + BS - 1) / BS;
-    // slice of windows scanned by this warp in phase B
-    const uint32_t slice = (W + NW - 1) / NW;
-    const uint32_t s_lo = min(warp * slice, W), s_hi = min(s_lo + slice, W);
-    const uint32_t per_lane = (slice + 31) / 32;
     const bool fast33 = p.fast33 != 0;
     uint32_t pp = 0, parity = 0;
     uint64_t tile = blockIdx.x;
@@ -130,47 +126,35 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
             }
         }
         __syncthreads();
-        // ---- phase B: every warp scans its slice of windows; lane l owns windows s_lo + l*per_lane + [0, per_lane)
-        {
-            uint32_t before = 0;  // entries (x8) of the windows in front of this warp's slice
-            for (uint32_t w = lane; w < s_lo; w += 32) before += hcur[w] & 0xFFFFu;
+        // ---- phase B: thread t owns window t (round r: window r*BS + t).  A warp's offset is the sum of the
+        // histogram in front of it, read redundantly (W/32 loads per lane + one warp reduction) instead of a second
+        // barrier; warps whose 32 windows lie beyond W skip the phase.  (The round-2 ncu capture of the first
+        // version, where every warp scanned a slice with a few active lanes, spent 32 % of the kernel here.)
+        for (uint32_t base = 0; base < W; base += BS) {
+            const uint32_t wfirst = base + warp * 32;  // first window of this warp in this round
+            if (wfirst >= W) break;
+            const uint32_t w = wfirst + lane;
+            const uint32_t mine = w < W ? (hcur[w] & 0xFFFFu) : 0u;  // bytes of sorted[] the window's run takes
+            uint32_t before = 0;
+            for (uint32_t x = lane; x < wfirst; x += 32) before += hcur[x] & 0xFFFFu;
 #pragma unroll
             for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-            const uint32_t w0 = s_lo + lane * per_lane;
-            uint32_t sum = 0;
-            for (uint32_t q = 0; q < per_lane; ++q)
-                if (w0 + q < s_hi) sum += hcur[w0 + q] & 0xFFFFu;
-            uint32_t incl = sum;
+            uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if ((int)lane >= o) incl += v;
             }
-            uint32_t run8 = before + incl - sum;  // byte offset of the run in sorted[]
-            for (uint32_t q = 0; q < per_lane; ++q) {
-                const uint32_t w = w0 + q;
-                if (w < s_hi) {
-                    const uint32_t need = (hcur[w] & 0xFFFFu) / kRankStep;
-                    uint32_t c = cur[w];
-                    if (need) {
-                        const uint32_t e = lim[w];
-                        if (c + need > e) {
-                            // hand back what is left of the old quota as sentinels, then reserve a new one
-                            const uint32_t stop = e < p.cap ? e : p.cap;
-                            for (uint32_t z = c; z < stop; ++z) p.stage[(size_t)w * p.cap + z] = kSentinel;
-                            const uint32_t take = need > p.quota ? need : p.quota;
-                            c = atomicAdd(p.cursors + w, take);
-                            lim[w] = c + take;
-                        }
-                        cur[w] = c + need;
-                        if (c + need > p.cap) tile_flags[0] = 1;  // benign race: every writer stores 1
-                    }
-                    tab[w] = Part4Tab{run8, w * p.cap + c - run8 / kRankStep};
-                    run8 += need * kRankStep;
-                    hist[pp ^ 1][w] = w << 16;  // last read in phase B of the previous tile
-                }
+            const uint32_t run8 = before + incl - mine;  // byte offset of the run in sorted[]
+            if (w < W) {
+                const uint32_t need = mine / kRankStep;
+                const uint32_t c = cur[w];  // entries this CTA has written to its sublist of window w so far
+                cur[w] = c + need;
+                if (c + need > p.sub_cap) tile_flags[0] = 1;  // benign race: every writer stores 1
+                tab[w] = Part4Tab{run8, (w * p.n_sub + blockIdx.x) * p.sub_cap + c - run8 / kRankStep};
+                hist[pp ^ 1][w] = w << 16;  // last read in phase B of the previous tile
+                if (w == W - 1) tile_flags[1] = (run8 + mine) / kRankStep;  // entries in the tile
             }
-            if (warp == NW - 1 && lane == 31) tile_flags[1] = run8 / kRankStep;  // this lane ends up with the total
         }
         __syncthreads();
         const bool slow = tile_flags[0] != 0;
@@ -212,9 +196,10 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
             for (uint32_t e = tid; e < total; e += BS) {
                 const uint2 v = sorted[e];
                 const Part4Tab t = tab[v.y];
-                const uint32_t pos = t.gdelta + e - v.y * p.cap;  // position inside window v.y's list
-                if (pos < p.cap) {
-                    __stcs(p.stage + (size_t)v.y * p.cap + pos, v.x);
+                const uint32_t first = (v.y * p.n_sub + blockIdx.x) * p.sub_cap;  // entry number of the sublist's start
+                const uint32_t pos = t.gdelta + e - first;                        // position inside the sublist
+                if (pos < p.sub_cap) {
+                    __stcs(p.stage + (size_t)first + pos, v.x);
                 } else {
                     part_overflow(p, ((uint64_t)v.y << p.window_log2) | v.x);
                 }
@@ -225,54 +210,56 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
         pp ^= 1;
     }
     __syncthreads();
-    for (uint32_t w = tid; w < W; w += BS) {
-        const uint32_t e = lim[w] < p.cap ? lim[w] : p.cap;
-        for (uint32_t q = cur[w]; q < e; ++q) p.stage[(size_t)w * p.cap + q] = kSentinel;
-    }
+    for (uint32_t w = tid; w < W; w += BS) p.counts[(size_t)w * p.n_sub + blockIdx.x] = min(cur[w], p.sub_cap);
 }
 
-// host-side launcher of bloom_part4 for a key batch of any layout.  512-key tiles only exist for K <= 8 (the sorted
-// tile of a larger K would not fit the 48 KB of static shared memory) and for 16-byte keys.
-template <int K>
-static cudaError_t launch_part4_k(bool big_tile, int grid, cudaStream_t stream, const DevKeys &dk, const Part2Dev &pd) {
-    // K <= 8: 56 registers, four 256-thread CTAs per SM plus room for one pass-2 CTA; K > 8: 72 registers, three CTAs
-    // (`grid` arrives sized for four per SM)
-    if (K > 8 && grid >= 4) grid = grid / 4 * 3;
-    if (is_fixed16(dk)) {
-        KeySrcFixed16 src{(const uint4 *)dk.data};
-        if constexpr (K <= 8) {
-            if (big_tile && grid >= 2) {
-                bloom_part4<K, 512, KeySrcFixed16><<<grid / 2, 512, 0, stream>>>(src, dk.n, pd);
-                return cudaSuccess;
-            }
-        }
-        bloom_part4<K, 256, KeySrcFixed16><<<grid, 256, 0, stream>>>(src, dk.n, pd);
-        return cudaSuccess;
+// host-side launcher of bloom_part4 for a key batch of any layout: pd.n_sub CTAs of `block` threads.  512-key
+// tiles only exist for K <= 8 (the sorted tile of a larger K would not fit the 48 KB of static shared memory) and
+// for 16-byte keys (part_big_tile).
+// Both passes ask for the largest shared-memory carveout: pass 2 (33 KB per CTA) has to fit NEXT TO the four resident
+// pass-1 CTAs of the following chunk, and an SM cannot change its L1/shared split while CTAs are resident -- with
+// the default heuristic split pass 1 left no room and the two passes silently ran one after the other.
+template <class Kern>
+static cudaError_t prefer_max_smem(Kern kern, size_t dyn) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess && dyn) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    return e;
+}
+
+template <int K, int BS, class KS>
+static cudaError_t launch_part4_inst(const KS &src, size_t dyn, cudaStream_t stream, uint64_t n, const PartDev &pd) {
+    static bool configured = false;  // per template instance
+    if (!configured) {
+        cudaError_t e = prefer_max_smem(bloom_part4<K, BS, KS>, dyn);
+        if (e != cudaSuccess) return e;
+        configured = true;
     }
-    const size_t dyn = kPart4StageBytes + 16;
-    if (dk.sym_width == 4) {
-        static bool attr4 = false;  // per template instance
-        if (!attr4) {
-            cudaError_t e = cudaFuncSetAttribute(bloom_part4<K, 256, KeySrcStaged<4>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e != cudaSuccess) return e;
-            attr4 = true;
-        }
-        bloom_part4<K, 256, KeySrcStaged<4>><<<grid, 256, dyn, stream>>>(KeySrcStaged<4>{dk}, dk.n, pd);
-    } else {
-        static bool attr1 = false;
-        if (!attr1) {
-            cudaError_t e = cudaFuncSetAttribute(bloom_part4<K, 256, KeySrcStaged<1>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e != cudaSuccess) return e;
-            attr1 = true;
-        }
-        bloom_part4<K, 256, KeySrcStaged<1>><<<grid, 256, dyn, stream>>>(KeySrcStaged<1>{dk}, dk.n, pd);
-    }
+    bloom_part4<K, BS, KS><<<(int)pd.n_sub, BS, dyn, stream>>>(src, n, pd);
     return cudaSuccess;
 }
 
-cudaError_t launch_part4(uint32_t k, bool big_tile, int grid, cudaStream_t stream, const DevKeys &dk, const Part2Dev &pd) {
-    switch (k) {
-#define PB_P4(KK) case KK: return launch_part4_k<KK>(big_tile, grid, stream, dk, pd);
+// host-side launcher of bloom_part4 for a key batch of any layout: pd.n_sub CTAs of `block` threads.  512-key
+// tiles only exist for K <= 8 (the sorted tile of a larger K would not fit the 48 KB of static shared memory) and
+// for 16-byte keys (part_big_tile).
+template <int K>
+static cudaError_t launch_part4_k(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd) {
+    if (is_fixed16(dk)) {
+        KeySrcFixed16 src{(const uint4 *)dk.data};
+        if constexpr (K <= 8) {
+            if (block == 512) return launch_part4_inst<K, 512>(src, 0, stream, dk.n, pd);
+        }
+        if (block != 256) return cudaErrorInvalidValue;
+        return launch_part4_inst<K, 256>(src, 0, stream, dk.n, pd);
+    }
+    if (block != 256) return cudaErrorInvalidValue;
+    const size_t dyn = kPart4StageBytes + 16;
+    if (dk.sym_width == 4) return launch_part4_inst<K, 256>(KeySrcStaged<4>{dk}, dyn, stream, dk.n, pd);
+    return launch_part4_inst<K, 256>(KeySrcStaged<1>{dk}, dyn, stream, dk.n, pd);
+}
+
+cudaError_t launch_part4(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd) {
+    switch (pd.k) {
+#define PB_P4(KK) case KK: return launch_part4_k<KK>(block, stream, dk, pd);
         PB_P4(1) PB_P4(2) PB_P4(3) PB_P4(4) PB_P4(5) PB_P4(6) PB_P4(7) PB_P4(8)
         PB_P4(9) PB_P4(10) PB_P4(11) PB_P4(12) PB_P4(13) PB_P4(14) PB_P4(15) PB_P4(16)
 #undef PB_P4

@@ -295,6 +295,18 @@ __global__ void __launch_bounds__(256) cms_join_kernel(int32_t *__restrict__ a, 
     }
 }
 
+// multi-GPU merge: int32 table -> int64 (exact sums across ranks), and the saturated way back (:380-391 for
+// non-negative tables: a chain of saturating joins equals min(sum, INT32_MAX))
+__global__ void __launch_bounds__(256) cms_widen_kernel(const int32_t *__restrict__ a, long long *__restrict__ out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = a[i];
+}
+__global__ void __launch_bounds__(256) cms_narrow_kernel(const long long *__restrict__ s, int32_t *__restrict__ out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const long long v = s[i];
+        out[i] = (int32_t)(v > kI32Max ? kI32Max : (v < kI32Min ? kI32Min : v));
+    }
+}
+
 // sum and sum-of-abs of an int64 array (saturating), for elements_added with per-key num_els on the device
 __global__ void __launch_bounds__(256) sum_i64_kernel(const int64_t *__restrict__ v, uint64_t n, long long *out_sum,
                                                       unsigned long long *out_abs) {
@@ -662,6 +674,28 @@ int pb_cms_join_buffer(pb_cms *c, const int32_t *other_dev, uint64_t count) {
     DeviceGuard g(ctx->device);
     cms_join_kernel<<<grid_for(ctx, count, 256, 8), 256, 0, ctx->stream>>>(c->bins, other_dev, count);
     PB_TRY(check_launch(ctx, "cms_join"));
+    c->abs_added = ~0ull;  // unknown from here on: take the careful add path
+    return PB_OK;
+}
+
+/* multi-GPU merge helpers: the table widened to int64 (input of one all-reduce), and a table loaded from int64
+ * sums with the reference's saturation */
+int pb_cms_widen(pb_cms *c, int64_t *out_dev, uint64_t count) {
+    PB_REQUIRE(c && out_dev, "NULL argument");
+    PB_REQUIRE(count == c->count, "expected %llu counters, got %llu", (unsigned long long)c->count, (unsigned long long)count);
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    cms_widen_kernel<<<grid_for(ctx, count, 256, 8), 256, 0, ctx->stream>>>(c->bins, (long long *)out_dev, count);
+    return check_launch(ctx, "cms_widen");
+}
+
+int pb_cms_load_sums(pb_cms *c, const int64_t *sums_dev, uint64_t count) {
+    PB_REQUIRE(c && sums_dev, "NULL argument");
+    PB_REQUIRE(count == c->count, "expected %llu counters, got %llu", (unsigned long long)c->count, (unsigned long long)count);
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    cms_narrow_kernel<<<grid_for(ctx, count, 256, 8), 256, 0, ctx->stream>>>((const long long *)sums_dev, c->bins, count);
+    PB_TRY(check_launch(ctx, "cms_load_sums"));
     c->abs_added = ~0ull;  // unknown from here on: take the careful add path
     return PB_OK;
 }

@@ -73,12 +73,14 @@ struct pb_ctx {
                                          // windows being updated stay L2 resident; 4 x 32 MiB at once thrashed: r1 sweep)
     int64_t bloom_part_tile = 0;         // keys per pass-1 tile: 0 auto (512 beyond 112 windows), 256, 512
     int64_t bloom_overlap = 1;           // run pass 2 of chunk i on aux_stream while pass 1 of chunk i+1 runs
-    int64_t bloom_part_version = 4;      // pass 1 of the partitioned insert: 4 = bloom_part4 (any key layout), 3 = round-1 kernel (cross-check)
+    int64_t bloom_part_ctas_per_sm = 4;  // pass 1: resident 256-thread CTAs per SM (registers allow 4 for k <= 8, 3 beyond)
+    int64_t bloom_min_chunks = 8;        // overlapped partitioned insert: split a batch into at least this many chunks
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics
     int64_t cms_hot_cache = 1;           // per-CTA shared-memory write-back cache for hot counters (safe path)
     int64_t cuckoo_serial = 0;           // 1: one-thread in-order cuckoo insert (reference append order)
+    int64_t p2p_timeout_ms = 20000;      // multi-GPU flag waits give up after this long (pb_p2p_check reports it)
     int64_t kernel_timing = 0;           // 1: bracket the hot kernels with CUDA events (bench roofline)
     std::vector<pb_timed_launch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -92,6 +94,7 @@ struct pb_ctx {
     pb_scratch part_cursors;   // bucket cursors
     pb_scratch small;          // counters and tiny results
     pb_scratch flush;          // L2 flush buffer
+    pb_scratch claim_set;      // cuckoo in-batch dedupe set
     void *pinned[2] = {nullptr, nullptr};  // pinned bounce buffers for pageable host memory
     size_t pinned_cap[2] = {0, 0};
     void *pinned_small = nullptr;          // 4 KiB pinned result area
@@ -179,5 +182,8 @@ typedef int (*chunk_fn)(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot
 int for_each_chunk(pb_ctx *ctx, const pb_keys *keys, chunk_fn fn, void *user, uint64_t max_chunk_keys = 0);
 
 int validate_keys(const pb_keys *keys);
+
+// default_fnv_1a rows of device-resident keys (pb_ctx.cu): out[i*depth + s] = fnv_1a(key_i, seed s)
+int hash_dev_keys(pb_ctx *ctx, const DevKeys &dk, uint32_t depth, uint64_t *out);
 
 }  // namespace pb

@@ -182,6 +182,29 @@ __global__ void __launch_bounds__(256) gen_rank_kernel(const uint64_t *ranks, ui
     }
 }
 
+// Zipf(a) ranks on the device (bench utility): the rejection sampler numpy's Generator.zipf uses
+// (Devroye, "Non-Uniform Random Variate Generation", p. 551), driven by a counter-based splitmix64 stream so that
+// rank i depends only on (seed, i).  Not reference code; the oracle is fed the very same buffer.
+__global__ void __launch_bounds__(256) gen_zipf_kernel(uint64_t seed, uint64_t first, uint64_t n, double a, uint64_t *out) {
+    const double am1 = a - 1.0, b = pow(2.0, am1);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t ctr = sm64(seed ^ sm64(first + i));
+        uint64_t x = 1;
+        for (int it = 0; it < 64; ++it) {
+            const double u = 1.0 - (double)(sm64(ctr++) >> 11) * (1.0 / 9007199254740992.0);  // (0, 1]
+            const double v = (double)(sm64(ctr++) >> 11) * (1.0 / 9007199254740992.0);
+            const double xf = floor(pow(u, -1.0 / am1));
+            if (xf > 9.2e18 || xf < 1.0) continue;
+            const double t = pow(1.0 + 1.0 / xf, am1);
+            if (v * xf * (t - 1.0) / (b - 1.0) <= t / b) {
+                x = (uint64_t)xf;
+                break;
+            }
+        }
+        out[i] = x;
+    }
+}
+
 template <int KG>
 __global__ void __launch_bounds__(256) hash_fixed16_kernel(const uint4 *keys, uint64_t n, uint32_t depth, uint64_t *out) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -221,6 +244,50 @@ __global__ void __launch_bounds__(kTileKeys) hash_staged_kernel(DevKeys dk, uint
     }
 }
 
+// fnv_1a(key, seed) / fnv_1a_32(key, seed) for an arbitrary seed (hashes.py:86-122): one hash per key from an explicit
+// start value.  Not a hot path (the filters use seeds 0..k-1 through the kernels above): one thread walks one key.
+template <int SYMW>
+__global__ void __launch_bounds__(256) hash_from_kernel(DevKeys dk, uint64_t h0, int bits32, uint64_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < dk.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t beg, end;
+        if (dk.offsets) {
+            beg = dk.offsets[i] - dk.base_symbol;
+            end = dk.offsets[i + 1] - dk.base_symbol;
+        } else {
+            beg = i * (uint64_t)dk.stride;
+            end = beg + dk.stride;
+        }
+        uint64_t h = h0;
+        for (uint64_t s = beg; s < end; ++s) {
+            const uint32_t sym = SYMW == 4 ? reinterpret_cast<const uint32_t *>(dk.data)[s] : (uint32_t)dk.data[s];
+            if (bits32) h = (uint32_t)(((uint32_t)h ^ sym) * 0x01000193u);  // hashes.py:116-121
+            else h = fnv_step(h, sym);                                    // hashes.py:99-102
+        }
+        out[i] = h;
+    }
+}
+
+struct HashFromArgs {
+    uint64_t h0;
+    int bits32;
+    uint64_t *out_dev, *out_host;
+};
+
+static int hash_from_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    HashFromArgs *a = (HashFromArgs *)user;
+    uint64_t *out = a->out_dev ? a->out_dev + first : nullptr;
+    if (!out) {
+        PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n * sizeof(uint64_t)));
+        out = (uint64_t *)ctx->out_stage[slot].p;
+    }
+    const int grid = grid_for(ctx, dk.n, 256, 8);
+    if (dk.sym_width == 4) hash_from_kernel<4><<<grid, 256, 0, ctx->stream>>>(dk, a->h0, a->bits32, out);
+    else hash_from_kernel<1><<<grid, 256, 0, ctx->stream>>>(dk, a->h0, a->bits32, out);
+    PB_TRY(check_launch(ctx, "hash_from"));
+    if (a->out_host) PB_CUDA(cudaMemcpyAsync(a->out_host + first, out, dk.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
 struct HashArgs {
     uint32_t depth;
     uint64_t *out_dev;   // device output for the whole batch (device-out) or nullptr
@@ -243,6 +310,20 @@ static int launch_hash(pb_ctx *ctx, const DevKeys &dk, uint32_t depth, uint64_t 
     return check_launch(ctx, "hash_keys");
 }
 
+// default_fnv_1a rows for device-resident keys of any layout: out[i*depth + s] (stream-ordered)
+int hash_dev_keys(pb_ctx *ctx, const DevKeys &dk, uint32_t depth, uint64_t *out) {
+    switch (pick_group(depth)) {
+        case 1: return launch_hash<1>(ctx, dk, depth, out);
+        case 2: return launch_hash<2>(ctx, dk, depth, out);
+        case 3: return launch_hash<3>(ctx, dk, depth, out);
+        case 4: return launch_hash<4>(ctx, dk, depth, out);
+        case 5: return launch_hash<5>(ctx, dk, depth, out);
+        case 6: return launch_hash<6>(ctx, dk, depth, out);
+        case 7: return launch_hash<7>(ctx, dk, depth, out);
+        default: return launch_hash<8>(ctx, dk, depth, out);
+    }
+}
+
 static int hash_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
     HashArgs *a = (HashArgs *)user;
     uint64_t *out = a->out_dev ? a->out_dev + first * a->depth : nullptr;
@@ -250,18 +331,7 @@ static int hash_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, 
         PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n * a->depth * sizeof(uint64_t)));
         out = (uint64_t *)ctx->out_stage[slot].p;
     }
-    int g = pick_group(a->depth);
-    int st;
-    switch (g) {
-        case 1: st = launch_hash<1>(ctx, dk, a->depth, out); break;
-        case 2: st = launch_hash<2>(ctx, dk, a->depth, out); break;
-        case 3: st = launch_hash<3>(ctx, dk, a->depth, out); break;
-        case 4: st = launch_hash<4>(ctx, dk, a->depth, out); break;
-        case 5: st = launch_hash<5>(ctx, dk, a->depth, out); break;
-        case 6: st = launch_hash<6>(ctx, dk, a->depth, out); break;
-        case 7: st = launch_hash<7>(ctx, dk, a->depth, out); break;
-        default: st = launch_hash<8>(ctx, dk, a->depth, out); break;
-    }
+    const int st = hash_dev_keys(ctx, dk, a->depth, out);
     PB_TRY(st);
     if (a->out_host)
         PB_CUDA(cudaMemcpyAsync(a->out_host + first * a->depth, out, dk.n * a->depth * sizeof(uint64_t),
@@ -348,6 +418,7 @@ int pb_ctx_destroy(pb_ctx *ctx) {
     scratch_release(ctx->part_cursors);
     scratch_release(ctx->small);
     scratch_release(ctx->flush);
+    scratch_release(ctx->claim_set);
     if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
     for (const pb_timed_launch &t : ctx->timed) {
         cudaEventDestroy(t.e0);
@@ -429,13 +500,15 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "bloom_window_log2_bits")) return &ctx->bloom_window_log2_bits;
     if (!strcmp(name, "stage_bytes")) return &ctx->stage_bytes;
     if (!strcmp(name, "bloom_apply_cpw_per_sm")) return &ctx->bloom_apply_cpw_per_sm;
-    if (!strcmp(name, "bloom_part_version")) return &ctx->bloom_part_version;
+    if (!strcmp(name, "bloom_min_chunks")) return &ctx->bloom_min_chunks;
+    if (!strcmp(name, "bloom_part_ctas_per_sm")) return &ctx->bloom_part_ctas_per_sm;
     if (!strcmp(name, "bloom_overlap")) return &ctx->bloom_overlap;
     if (!strcmp(name, "bloom_part_tile")) return &ctx->bloom_part_tile;
     if (!strcmp(name, "h2d_chunk_keys")) return &ctx->h2d_chunk_keys;
     if (!strcmp(name, "cms_aggregate")) return &ctx->cms_aggregate;
     if (!strcmp(name, "cms_hot_cache")) return &ctx->cms_hot_cache;
     if (!strcmp(name, "cuckoo_serial")) return &ctx->cuckoo_serial;
+    if (!strcmp(name, "p2p_timeout_ms")) return &ctx->p2p_timeout_ms;
     if (!strcmp(name, "kernel_timing")) return &ctx->kernel_timing;
     return nullptr;
 }
@@ -525,6 +598,16 @@ int pb_hash_keys(pb_ctx *ctx, const pb_keys *keys, uint32_t depth, uint64_t *out
     return PB_OK;
 }
 
+int pb_hash_keys_from(pb_ctx *ctx, const pb_keys *keys, uint64_t start_value, int bits, uint64_t *out, int out_on_device) {
+    PB_REQUIRE(ctx && out, "NULL argument");
+    PB_REQUIRE(bits == 64 || bits == 32, "bits must be 64 or 32");
+    DeviceGuard g(ctx->device);
+    HashFromArgs a{start_value, bits == 32 ? 1 : 0, out_on_device ? out : nullptr, out_on_device ? nullptr : out};
+    PB_TRY(for_each_chunk(ctx, keys, hash_from_chunk, &a));
+    if (!out_on_device) PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
 int pb_gen_uniform_keys(pb_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, void *out_dev) {
     PB_REQUIRE(ctx && (out_dev || n == 0), "NULL argument");
     PB_REQUIRE(((uintptr_t)out_dev & 15u) == 0, "out_dev must be 16-byte aligned");
@@ -532,6 +615,15 @@ int pb_gen_uniform_keys(pb_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, 
     DeviceGuard g(ctx->device);
     gen_uniform_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(seed, first, n, (ulonglong2 *)out_dev);
     return check_launch(ctx, "gen_uniform_keys");
+}
+
+int pb_gen_zipf_ranks(pb_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, double a, uint64_t *out_ranks_dev) {
+    PB_REQUIRE(ctx && (out_ranks_dev || n == 0), "NULL argument");
+    PB_REQUIRE(a > 1.0, "the Zipf exponent must be > 1");
+    if (n == 0) return PB_OK;
+    DeviceGuard g(ctx->device);
+    gen_zipf_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(seed, first, n, a, out_ranks_dev);
+    return check_launch(ctx, "gen_zipf_ranks");
 }
 
 int pb_gen_rank_keys(pb_ctx *ctx, const uint64_t *ranks_dev, uint64_t n, void *out_dev) {

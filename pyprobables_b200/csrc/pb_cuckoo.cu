@@ -11,7 +11,7 @@
 //
 // add() for a batch runs as three kernels:
 //   1. claim+filter  hash key -> fp (:499-500); one thread per *distinct* fp of the batch wins a claim
-//                    bit (atomicOr on a 2^fp_bits-bit scratch bitmap: exact in-batch dedupe); the winner
+//                    (an exact set in scratch memory: one atomicCAS / atomicOr per key); the winner
 //                    looks the fp up in its two buckets (:300-302, :440-446) and, when absent, appends
 //                    it to a compact list of fingerprints to insert.
 //   2. insert        one thread per new fp: CAS into the first empty slot of idx_1, then idx_2
@@ -19,7 +19,8 @@
 //                    atomicExch -- every fingerprint is always either in a slot or in exactly one
 //                    thread's hand, so nothing is duplicated or lost.  Walks that run out of swaps hand
 //                    their homeless fingerprint back to the caller (:392, :508-516).
-//   3. unclaim       clears the claim bits again (memset for big batches, per-fp for small ones).
+//   3. the claim scratch is cleared again.  Small batches claim in an open-addressing set sized to the batch
+//      (context scratch); only batches whose set would be larger use the 2^fp_bits-bit bitmap (allocated lazily).
 // Because kernel 2 only ever sees fingerprints that are distinct and absent, no presence check has to
 // race with an eviction in flight.
 // "cuckoo_serial" (context option) replaces 1-3 by a one-thread kernel that inserts in key order, which
@@ -42,8 +43,10 @@ struct pb_cuckoo {
     uint32_t *slots = nullptr;
     uint64_t nslots = 0;
     uint32_t *zero_flag = nullptr;  // device word: 1 when fingerprint 0 is stored
-    uint32_t *claim = nullptr;      // 2^fp_bits bits of in-batch claim scratch
+    uint32_t *claim = nullptr;      // 2^fp_bits bits of in-batch claim scratch (large batches only, allocated on first use)
     uint64_t claim_words = 0;
+    uint64_t *alt = nullptr;        // pre-indexed mode: idx_2 per slot (allocated by the first pre-indexed call)
+    uint64_t n_stored = 0;          // host mirror of the number of stored fingerprints is kept by the caller
     FastMod fm;
 };
 
@@ -52,10 +55,27 @@ namespace pb {
 struct CuckooDev {
     uint32_t *slots;
     uint32_t *zero_flag;
-    uint32_t *claim;
+    uint32_t *claim;      // in-batch dedupe scratch: a 2^fp_bits-bit bitmap, or (claim_mask != 0) an open-addressing set
+    uint32_t claim_mask;  // set mode: number of u32 entries - 1 (power of two, >= 4 x batch)
+    uint64_t *alt;        // pre-indexed filters (custom hash_function): idx_2 of the fingerprint in every slot
     FastMod fm;
     uint32_t bucket_size, max_swaps, fp_bits;
 };
+
+// exactly one thread per distinct fingerprint of the batch gets `true` (fp != 0)
+__device__ __forceinline__ bool claim_fp(const CuckooDev &c, uint32_t fp) {
+    if (c.claim_mask == 0u) {
+        const uint32_t bit = 1u << (fp & 31u);
+        return (atomicOr(c.claim + (fp >> 5), bit) & bit) == 0u;
+    }
+    uint32_t slot = (fp * 0x9E3779B1u) & c.claim_mask;
+    for (;;) {
+        const uint32_t old = atomicCAS(c.claim + slot, 0u, fp);
+        if (old == 0u) return true;
+        if (old == fp) return false;
+        slot = (slot + 1u) & c.claim_mask;
+    }
+}
 
 struct CuckooCounters {  // device-resident, zeroed per call
     unsigned long long n_new;     // fingerprints handed to the insert kernel
@@ -154,9 +174,7 @@ __device__ __forceinline__ void claim_filter(const CuckooDev &c, uint32_t fp, bo
             // the zero fingerprint lives in the flag word; the flag itself is the claim
             if (atomicExch(c.zero_flag, 1u) == 0u) atomicAdd(&cnt->n_placed, 1ull);
         } else {
-            const uint32_t bit = 1u << (fp & 31u);
-            const uint32_t old = atomicOr(c.claim + (fp >> 5), bit);
-            if ((old & bit) == 0u) {  // this thread owns fp for the batch
+            if (claim_fp(c, fp)) {  // this thread owns fp for the batch
                 uint64_t i1, i2;
                 cuckoo_buckets(c, fp, i1, i2);
                 const bool in1 = bucket_has<BS>(c, i1, fp);  // both probes in flight together (no short circuit)
@@ -260,15 +278,6 @@ __global__ void __launch_bounds__(256) cuckoo_insert_kernel(const uint32_t *__re
     if (placed) atomicAdd(&cnt->n_placed, placed);  // one per thread: noise next to the table traffic
 }
 
-// ---- kernel 3: release the claim bits of a small batch ---------------------------------------------------
-__global__ void __launch_bounds__(256) cuckoo_unclaim_kernel(const uint32_t *__restrict__ fps, uint64_t n, uint32_t fp_bits,
-                                                             uint32_t *claim) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], fp_bits);
-        claim[fp >> 5] = 0u;  // whole word: every bit of it that is set belongs to this batch
-    }
-}
-
 // ---- serial restatement on the device (one thread, key order) -----------------------------------------
 template <int BS>
 __global__ void cuckoo_serial_kernel(const uint32_t *__restrict__ fps, uint64_t n, CuckooDev c, uint64_t rng_seed,
@@ -323,6 +332,119 @@ __global__ void __launch_bounds__(256)
         out[i] = cuckoo_lookup<BS>(c, cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits));
 }
 
+// ---- remove (cuckoo.py:317-330): clear the slot holding fp in idx_1, else in idx_2 -----------------------------
+template <int BS>
+__device__ __forceinline__ bool bucket_take(const CuckooDev &c, uint64_t b, uint32_t fp) {
+    uint32_t *s = c.slots + b * c.bucket_size;
+    for (uint32_t j = 0; j < c.bucket_size; ++j)
+        if (__ldcg(s + j) == fp && atomicCAS(s + j, fp, 0u) == fp) return true;  // one winner per stored copy
+    return false;
+}
+
+// i2_in == nullptr: idx_2 from the built-in FNV of the decimal digits; else the caller's (custom hash_function)
+template <int BS>
+__global__ void __launch_bounds__(256) cuckoo_remove_fps(const uint32_t *__restrict__ fps, const uint64_t *__restrict__ i2_in, uint64_t n,
+                                                         CuckooDev c, uint8_t *__restrict__ out, CuckooCounters *cnt) {
+    unsigned long long removed = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits);
+        bool hit;
+        if (fp == 0u) {
+            hit = atomicExch(c.zero_flag, 0u) != 0u;
+        } else {
+            uint64_t i1, i2;
+            cuckoo_buckets(c, fp, i1, i2);
+            if (i2_in) i2 = i2_in[i];
+            hit = bucket_take<BS>(c, i1, fp) || bucket_take<BS>(c, i2, fp);  // :325-328 (idx_1 first)
+        }
+        out[i] = (uint8_t)hit;
+        removed += hit;
+    }
+    if (removed) atomicAdd(&cnt->n_placed, removed);
+}
+
+// ---- pre-indexed filters (a custom hash_function: idx_2 = hash_function(str(fp)) % capacity, cuckoo.py:489, cannot
+// be evaluated on the device).  The caller supplies idx_2 with every fingerprint and the table keeps the idx_2 of
+// every stored fingerprint next to it (`alt`), which is what the eviction walk needs for its victims (:383-385).
+// One thread, key order: these filters are bound by the user's Python hash anyway, and the order makes the
+// result the reference's exactly (append order, :448-453).
+template <int BS>
+__device__ __forceinline__ bool indexed_place(const CuckooDev &c, uint64_t b, uint32_t fp, uint64_t i2) {
+    uint32_t *s = c.slots + b * c.bucket_size;
+    for (uint32_t j = 0; j < c.bucket_size; ++j) {
+        if (s[j] == 0u) {
+            s[j] = fp;
+            c.alt[b * c.bucket_size + j] = i2;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int BS>
+__global__ void cuckoo_serial_indexed(const uint32_t *__restrict__ fps, const uint64_t *__restrict__ i2_in, uint64_t n, CuckooDev c,
+                                      uint64_t rng, uint32_t *__restrict__ failed_fp, uint64_t *__restrict__ failed_i2,
+                                      uint64_t failed_cap, CuckooCounters *cnt) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits);
+        if (fp == 0u) {
+            if (*c.zero_flag == 0u) {
+                *c.zero_flag = 1u;
+                cnt->n_placed++;
+            }
+            continue;
+        }
+        uint64_t b2 = i2_in[i];
+        const uint64_t b1 = fastmod((uint64_t)fp, c.fm);
+        if (bucket_has<BS>(c, b1, fp) || bucket_has<BS>(c, b2, fp)) continue;  // :300-302
+        cnt->n_new++;
+        bool done = indexed_place<BS>(c, b1, fp, b2) || indexed_place<BS>(c, b2, fp, b2);  // :363-368
+        if (!done) {
+            rng = sm64(rng ^ fp);
+            uint64_t idx = (rng & 1ull) ? b2 : b1;  // :373
+            for (uint32_t s = 0; s < c.max_swaps && !done; ++s) {
+                rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+                const uint64_t pos = idx * c.bucket_size + (uint32_t)(((rng >> 33) * (uint64_t)c.bucket_size) >> 31);  // :377
+                const uint32_t victim = c.slots[pos];
+                const uint64_t victim_i2 = c.alt[pos];
+                c.slots[pos] = fp;  // :379-380
+                c.alt[pos] = b2;
+                fp = victim;
+                b2 = victim_i2;
+                const uint64_t a = fastmod((uint64_t)fp, c.fm);  // :383
+                idx = (idx == a) ? b2 : a;                       // :385
+                done = indexed_place<BS>(c, idx, fp, b2);        // :387-388
+            }
+        }
+        if (done) {
+            cnt->n_placed++;
+        } else {
+            if (cnt->n_failed < failed_cap) {
+                failed_fp[cnt->n_failed] = fp;
+                failed_i2[cnt->n_failed] = b2;
+            }
+            cnt->n_failed++;
+        }
+        __threadfence();
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) cuckoo_check_indexed(const uint32_t *__restrict__ fps, const uint64_t *__restrict__ i2_in, uint64_t n,
+                                                            CuckooDev c, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits);
+        if (fp == 0u) {
+            out[i] = (uint8_t)(__ldcg(c.zero_flag) != 0u);
+        } else {
+            const bool a = bucket_has<BS>(c, fastmod((uint64_t)fp, c.fm), fp);
+            const bool b = bucket_has<BS>(c, i2_in[i], fp);
+            out[i] = (uint8_t)(a | b);
+        }
+    }
+}
+
 // _generate_fingerprint_info (:492-506) from fingerprints
 __global__ void __launch_bounds__(256) cuckoo_info_kernel(const uint32_t *__restrict__ fps, uint64_t n, CuckooDev c,
                                                           uint64_t *__restrict__ i1, uint64_t *__restrict__ i2) {
@@ -344,6 +466,8 @@ static CuckooDev dev_view(const pb_cuckoo *c) {
     d.slots = c->slots;
     d.zero_flag = c->zero_flag;
     d.claim = c->claim;
+    d.claim_mask = 0;
+    d.alt = c->alt;
     d.fm = c->fm;
     d.bucket_size = c->bucket_size;
     d.max_swaps = c->max_swaps;
@@ -404,20 +528,29 @@ static int add_fps_device(pb_cuckoo *c, const uint4 *fused_keys, uint32_t *fps_d
         PB_BS_DISPATCH(c, cuckoo_serial_kernel, 1, 32, fps_dev, n, cd, seed, failed, n, cnt);
         PB_TRY(check_launch(ctx, "cuckoo_serial"));
     } else {
-        PB_TRY(ensure_claim(c));
-        const CuckooDev cd2 = dev_view(c);
+        // in-batch dedupe scratch: an exact open-addressing set of >= 4n entries in the context's scratch for batches
+        // whose set is smaller than the 2^fp_bits-bit bitmap (512 MiB for 32-bit fingerprints), the bitmap otherwise
+        CuckooDev cd2 = dev_view(c);
+        const uint64_t bitmap_bytes = c->fp_bits >= 5 ? (1ull << (c->fp_bits - 3)) : 4ull;
+        uint64_t set_entries = 64;
+        while (set_entries < 4 * n) set_entries <<= 1;
+        const bool use_set = set_entries * 4 < bitmap_bytes;
+        if (use_set) {
+            PB_TRY(scratch_reserve(ctx, ctx->claim_set, set_entries * 4));
+            PB_CUDA(cudaMemsetAsync(ctx->claim_set.p, 0, set_entries * 4, ctx->stream));
+            cd2.claim = (uint32_t *)ctx->claim_set.p;
+            cd2.claim_mask = (uint32_t)(set_entries - 1);
+        } else {
+            PB_TRY(ensure_claim(c));
+            cd2.claim = c->claim;
+        }
         const int grid = grid_for(ctx, n, 256, 8);
         if (fused_keys) PB_BS_DISPATCH(c, cuckoo_claim_fixed16, grid, 256, fused_keys, n, cd2, fps_dev, newlist, cnt);
         else PB_BS_DISPATCH(c, cuckoo_claim_fps, grid, 256, fps_dev, n, cd2, newlist, cnt);
         PB_TRY(check_launch(ctx, "cuckoo_claim"));
         PB_BS_DISPATCH(c, cuckoo_insert_kernel, grid, 256, newlist, &cnt->n_new, 0, 0, cd2, seed, failed, n, cnt);
         PB_TRY(check_launch(ctx, "cuckoo_insert"));
-        if (n * 64 < c->claim_words * 4) {
-            cuckoo_unclaim_kernel<<<grid, 256, 0, ctx->stream>>>(fps_dev, n, c->fp_bits, c->claim);
-            PB_TRY(check_launch(ctx, "cuckoo_unclaim"));
-        } else {
-            PB_CUDA(cudaMemsetAsync(c->claim, 0, c->claim_words * 4, ctx->stream));
-        }
+        if (!use_set) PB_CUDA(cudaMemsetAsync(c->claim, 0, c->claim_words * 4, ctx->stream));
     }
     // results (small D2H; this call is synchronous by contract because failures must be reported)
     CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
@@ -602,6 +735,7 @@ int pb_cuckoo_destroy(pb_cuckoo *c) {
     cudaFree(c->slots);
     cudaFree(c->zero_flag);
     if (c->claim) cudaFree(c->claim);
+    if (c->alt) cudaFree(c->alt);
     delete c;
     return PB_OK;
 }
@@ -700,6 +834,189 @@ int pb_cuckoo_fingerprint_info(pb_cuckoo *c, const pb_keys *keys, uint32_t *fp, 
     // host outputs are copied back per chunk from per-slot scratch: keep chunks in step with the slots
     PB_TRY(for_each_chunk(c->ctx, keys, cuckoo_info_chunk, &a));
     if (!out_on_device) PB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    return PB_OK;
+}
+
+// stage a host array on the device (aux/out scratch slot `which`)
+static int stage_host(pb_ctx *ctx, pb_scratch &sc, const void *host, size_t bytes, void **dev) {
+    PB_TRY(scratch_reserve(ctx, sc, bytes ? bytes : 16));
+    if (bytes) PB_CUDA(cudaMemcpyAsync(sc.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = sc.p;
+    return PB_OK;
+}
+
+static int ensure_alt(pb_cuckoo *c) {
+    if (c->alt) return PB_OK;
+    PB_CUDA(cudaMalloc(&c->alt, ((c->nslots + 3) & ~(uint64_t)3) * 8));
+    PB_CUDA(cudaMemsetAsync(c->alt, 0, c->nslots * 8, c->ctx->stream));
+    return PB_OK;
+}
+
+// CuckooFilter.remove (cuckoo.py:317-330) for every key: out[i] = 1 when a stored copy of the key's fingerprint was
+// cleared.  Equal keys inside one batch: exactly one of them wins (the reference: the first).
+int pb_cuckoo_remove_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device, uint64_t *n_removed) {
+    PB_REQUIRE(c && keys && n_removed, "NULL argument");
+    PB_REQUIRE(out || keys->n == 0, "out is NULL");
+    PB_REQUIRE(keys->on_device || !out_on_device, "device output needs device keys");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    *n_removed = 0;
+    if (keys->n == 0) return validate_keys(keys);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    CuckooCounters *cnt = counters_dev(ctx);
+    PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(CuckooCounters), ctx->stream));
+    struct Args {
+        pb_cuckoo *c;
+        uint8_t *out_dev, *out_host;
+        CuckooCounters *cnt;
+    } a{c, out_on_device ? out : nullptr, out_on_device ? nullptr : out, cnt};
+    auto fn = [](pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) -> int {
+        Args *a = (Args *)user;
+        pb_cuckoo *c = a->c;
+        PB_TRY(scratch_reserve(ctx, ctx->aux_stage[slot], dk.n * 4));
+        uint32_t *fps = (uint32_t *)ctx->aux_stage[slot].p;
+        if (is_fixed16(dk)) {
+            cuckoo_fp_fixed16<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, c->fp_bits, fps);
+        } else {
+            const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+            const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+            if (dk.sym_width == 4) cuckoo_fp_staged<4><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+            else cuckoo_fp_staged<1><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+        }
+        PB_TRY(check_launch(ctx, "cuckoo_fp"));
+        uint8_t *o = a->out_dev ? a->out_dev + first : nullptr;
+        if (!o) {
+            PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n));
+            o = (uint8_t *)ctx->out_stage[slot].p;
+        }
+        const CuckooDev cd = dev_view(c);
+        PB_BS_DISPATCH(c, cuckoo_remove_fps, grid_for(ctx, dk.n, 256, 8), 256, fps, (const uint64_t *)nullptr, dk.n, cd, o, a->cnt);
+        PB_TRY(check_launch(ctx, "cuckoo_remove"));
+        if (a->out_host) PB_CUDA(cudaMemcpyAsync(a->out_host + first, o, dk.n, cudaMemcpyDeviceToHost, ctx->stream));
+        return PB_OK;
+    };
+    PB_TRY(for_each_chunk(ctx, keys, fn, &a));
+    CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
+    PB_CUDA(cudaMemcpyAsync(h, cnt, sizeof(CuckooCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_removed = h->n_placed;
+    return PB_OK;
+}
+
+// ---- pre-indexed entry points (custom hash_function: the caller hashes, see cuckoo_serial_indexed); host arrays
+int pb_cuckoo_add_indexed(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint64_t *n_added, uint64_t *n_failed,
+                          uint32_t *failed_fps, uint64_t *failed_i2, uint64_t failed_cap) {
+    PB_REQUIRE(c && n_added && n_failed && ((fps && i2) || n == 0), "NULL argument");
+    *n_added = *n_failed = 0;
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(ensure_alt(c));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    CuckooCounters *cnt = counters_dev(ctx);
+    PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(CuckooCounters), ctx->stream));
+    void *dfp, *di2;
+    PB_TRY(stage_host(ctx, ctx->out_stage[0], fps, n * 4, &dfp));
+    PB_TRY(stage_host(ctx, ctx->aux_stage[0], i2, n * 8, &di2));
+    const uint64_t fcap = std::max<uint64_t>(failed_cap, 1);
+    PB_TRY(scratch_reserve(ctx, ctx->out_stage[1], fcap * 4));
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[1], fcap * 8));
+    const uint64_t seed = c->rng_seed + (++c->epoch) * 0xD1B54A32D192ED03ULL;
+    const CuckooDev cd = dev_view(c);
+    PB_BS_DISPATCH(c, cuckoo_serial_indexed, 1, 32, (const uint32_t *)dfp, (const uint64_t *)di2, n, cd, seed,
+                   (uint32_t *)ctx->out_stage[1].p, (uint64_t *)ctx->aux_stage[1].p, fcap, cnt);
+    PB_TRY(check_launch(ctx, "cuckoo_serial_indexed"));
+    CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
+    PB_CUDA(cudaMemcpyAsync(h, cnt, sizeof(CuckooCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_added = h->n_placed;
+    *n_failed = h->n_failed;
+    if (h->n_failed) {
+        const uint64_t take = std::min<uint64_t>(h->n_failed, (failed_fps && failed_i2) ? failed_cap : 0);
+        if (take) {
+            PB_CUDA(cudaMemcpyAsync(failed_fps, ctx->out_stage[1].p, take * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaMemcpyAsync(failed_i2, ctx->aux_stage[1].p, take * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        set_error("The CuckooFilter is currently full (%llu fingerprints left homeless)", (unsigned long long)h->n_failed);
+        return PB_ERR_CUCKOO_FULL;
+    }
+    return PB_OK;
+}
+
+int pb_cuckoo_check_indexed(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint8_t *out) {
+    PB_REQUIRE(c && ((fps && i2 && out) || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    void *dfp, *di2;
+    PB_TRY(stage_host(ctx, ctx->out_stage[0], fps, n * 4, &dfp));
+    PB_TRY(stage_host(ctx, ctx->aux_stage[0], i2, n * 8, &di2));
+    PB_TRY(scratch_reserve(ctx, ctx->out_stage[1], n));
+    const CuckooDev cd = dev_view(c);
+    PB_BS_DISPATCH(c, cuckoo_check_indexed, grid_for(ctx, n, 256, 8), 256, (const uint32_t *)dfp, (const uint64_t *)di2, n, cd,
+                   (uint8_t *)ctx->out_stage[1].p);
+    PB_TRY(check_launch(ctx, "cuckoo_check_indexed"));
+    PB_CUDA(cudaMemcpyAsync(out, ctx->out_stage[1].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_cuckoo_remove_indexed(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint8_t *out, uint64_t *n_removed) {
+    PB_REQUIRE(c && n_removed && ((fps && i2 && out) || n == 0), "NULL argument");
+    *n_removed = 0;
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    CuckooCounters *cnt = counters_dev(ctx);
+    PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(CuckooCounters), ctx->stream));
+    void *dfp, *di2;
+    PB_TRY(stage_host(ctx, ctx->out_stage[0], fps, n * 4, &dfp));
+    PB_TRY(stage_host(ctx, ctx->aux_stage[0], i2, n * 8, &di2));
+    PB_TRY(scratch_reserve(ctx, ctx->out_stage[1], n));
+    const CuckooDev cd = dev_view(c);
+    PB_BS_DISPATCH(c, cuckoo_remove_fps, grid_for(ctx, n, 256, 8), 256, (const uint32_t *)dfp, (const uint64_t *)di2, n, cd,
+                   (uint8_t *)ctx->out_stage[1].p, cnt);
+    PB_TRY(check_launch(ctx, "cuckoo_remove"));
+    CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
+    PB_CUDA(cudaMemcpyAsync(out, ctx->out_stage[1].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(h, cnt, sizeof(CuckooCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_removed = h->n_placed;
+    return PB_OK;
+}
+
+// idx_2 of the fingerprint in every slot, for a table that was uploaded (a file written by the reference)
+int pb_cuckoo_set_alt(pb_cuckoo *c, const uint64_t *alt, uint64_t count) {
+    PB_REQUIRE(c && alt, "NULL argument");
+    PB_REQUIRE(count == c->nslots, "expected %llu entries, got %llu", (unsigned long long)c->nslots, (unsigned long long)count);
+    DeviceGuard g(c->ctx->device);
+    PB_TRY(ensure_alt(c));
+    PB_CUDA(cudaMemcpyAsync(c->alt, alt, count * 8, cudaMemcpyHostToDevice, c->ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    return PB_OK;
+}
+
+// an empty table of new_capacity buckets (pre-indexed filters expand by re-inserting from the host, :455-481)
+int pb_cuckoo_resize(pb_cuckoo *c, uint64_t new_capacity) {
+    PB_REQUIRE(c && new_capacity >= 1, "bad argument");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    uint32_t *new_slots = nullptr;
+    uint64_t new_n = 0;
+    PB_TRY(cuckoo_alloc_table(ctx, new_capacity, c->bucket_size, &new_slots, &new_n));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(cudaFree(c->slots));
+    if (c->alt) {
+        PB_CUDA(cudaFree(c->alt));
+        c->alt = nullptr;
+    }
+    c->slots = new_slots;
+    c->nslots = new_n;
+    c->capacity = new_capacity;
+    c->fm = make_fastmod(new_capacity);
+    PB_CUDA(cudaMemsetAsync(c->zero_flag, 0, 4, ctx->stream));
     return PB_OK;
 }
 

@@ -4,6 +4,12 @@
 Parity contract (see csrc/pb_cuckoo.cu): the *set of stored fingerprints*, `elements_added` and every
 `check` result equal the reference's; slot placement inside the table is free, as it is in the reference
 itself (its eviction walk draws from Python's unseeded global RNG, cuckoo.py:373/:377).
+
+A custom `hash_function` decides BOTH the fingerprint and idx_2 = hash_function(str(fingerprint)) % capacity
+(cuckoo.py:489, :499): such filters run *pre-indexed* -- the host evaluates the user's function (that is the plugin),
+ships (fingerprint, idx_2) pairs, and the device keeps the idx_2 of every stored fingerprint next to it so that the
+eviction walk can move victims without re-hashing them.  A filter exported by the reference with any hash function
+therefore loads and answers here exactly as it does there.
 """
 
 from __future__ import annotations
@@ -175,7 +181,23 @@ class CuckooFilter:
     def fingerprint_size(self, val: int):
         if not 1 <= val <= 4:
             raise ValueError(f"{self.__class__.__name__}: fingerprint size must be between 1 and 4")
-        self._fingerprint_bits = val * 8
+        self._set_fingerprint_bits(val * 8)
+
+    def _set_fingerprint_bits(self, bits: int) -> None:
+        """the device handle carries the fingerprint mask: changing it on a live filter re-creates the handle around
+        the same table (the reference only changes the mask applied to new keys, cuckoo.py:276-285)"""
+        old = getattr(self, "_fingerprint_bits", None)
+        self._fingerprint_bits = bits
+        if getattr(self, "_h", None) is None or old == bits:
+            return
+        if self._inserted == 0:
+            self._create()
+            return
+        slots, z = self.slots_numpy()
+        self._create()
+        flat = np.ascontiguousarray(slots.reshape(-1))
+        _native.call("pb_cuckoo_upload", self._h, C.c_void_p(flat.ctypes.data), flat.size, int(z))
+        self._upload_alt(flat)
 
     def load_factor(self) -> float:
         return self.elements_added / (self.capacity * self.bucket_size)
@@ -221,10 +243,20 @@ class CuckooFilter:
         )
 
     # ------------------------------------------------------------------ hot path
-    def _plugin_fingerprints(self, keys) -> np.ndarray:
-        """custom hash_function: fp = low fp_bits of hash_function(key) (cuckoo.py:499-500) on the host"""
+    def _plugin_pairs(self, keys):
+        """custom hash_function: fp = low fp_bits of hash_function(key) (cuckoo.py:499-500) and
+        idx_2 = hash_function(str(fp)) % capacity (:489), on the host -- the user's function IS the plugin"""
         mask = (1 << self._fingerprint_bits) - 1
-        return np.asarray([self._hash_func(k) & mask for k in keys], dtype=np.uint32)
+        fps = [self._hash_func(k) & mask for k in keys]
+        return np.asarray(fps, dtype=np.uint32), self._plugin_alt(fps)
+
+    def _plugin_alt(self, fps) -> np.ndarray:
+        cap = self._capacity
+        return np.asarray([self._hash_func(str(int(fp))) % cap for fp in fps], dtype=np.uint64)
+
+    @staticmethod
+    def _as_list(keys):
+        return [keys] if isinstance(keys, (str, bytes, bytearray, memoryview)) else list(keys)
 
     def _handle_failures(self, status_full: bool, n_failed: int, failed: np.ndarray) -> None:
         """_deal_with_insertion (cuckoo.py:508-516) for a batch"""
@@ -244,6 +276,8 @@ class CuckooFilter:
     def _add_fps_raw(self, fps: np.ndarray) -> np.ndarray:
         """insert fingerprints; returns the homeless ones (empty when all went in)"""
         fps = np.ascontiguousarray(fps, dtype=np.uint32)
+        if not self._fused:
+            return self._add_pairs(fps, self._plugin_alt(fps))
         n_added, n_failed = C.c_uint64(0), C.c_uint64(0)
         failed = np.empty(max(fps.size, 1), dtype=np.uint32)
         st = _native.lib().pb_cuckoo_add_fingerprints(
@@ -257,13 +291,27 @@ class CuckooFilter:
             raise CuckooFilterFullError(f"The {self.__class__.__name__} failed to expand")
         return failed[: n_failed.value].copy()
 
+    def _add_pairs(self, fps: np.ndarray, alt: np.ndarray) -> np.ndarray:
+        """pre-indexed insert (key order); returns the homeless fingerprints"""
+        n_added, n_failed = C.c_uint64(0), C.c_uint64(0)
+        failed = np.empty(max(fps.size, 1), dtype=np.uint32)
+        failed_alt = np.empty(max(fps.size, 1), dtype=np.uint64)
+        st = _native.lib().pb_cuckoo_add_indexed(
+            self._h, C.c_void_p(fps.ctypes.data), C.c_void_p(alt.ctypes.data), fps.size, C.byref(n_added), C.byref(n_failed),
+            C.c_void_p(failed.ctypes.data), C.c_void_p(failed_alt.ctypes.data), failed.size,
+        )
+        if st not in (_native.PB_OK, _native.PB_ERR_CUCKOO_FULL):
+            _native.check(st)
+        self._inserted += n_added.value
+        return failed[: n_failed.value].copy()
+
     def add_many(self, keys) -> None:
         """CuckooFilter.add (cuckoo.py:291-304) for every key.  With auto_expand the table grows by
         expansion_rate until every fingerprint is stored; without it CuckooFilterFullError is raised after
         the batch (the fingerprints that did fit stay stored, as they would in the reference up to the
         failing key)."""
-        n_added, n_failed = C.c_uint64(0), C.c_uint64(0)
         if self._fused:
+            n_added, n_failed = C.c_uint64(0), C.c_uint64(0)
             kb = pack_keys(keys)
             if kb.n == 0:
                 return
@@ -272,21 +320,16 @@ class CuckooFilter:
             st = _native.lib().pb_cuckoo_add_keys(
                 self._h, kb.ref(), C.byref(n_added), C.byref(n_failed), C.c_void_p(failed.ctypes.data), failed.size
             )
-        else:
-            if isinstance(keys, (str, bytes, bytearray, memoryview)):
-                keys = [keys]
-            fps = self._plugin_fingerprints(keys)
-            if fps.size == 0:
-                return
-            failed = np.empty(fps.size, dtype=np.uint32)
-            st = _native.lib().pb_cuckoo_add_fingerprints(
-                self._h, C.c_void_p(fps.ctypes.data), fps.size, 0, C.byref(n_added), C.byref(n_failed),
-                C.c_void_p(failed.ctypes.data), failed.size,
-            )
-        if st not in (_native.PB_OK, _native.PB_ERR_CUCKOO_FULL):
-            _native.check(st)
-        self._inserted += n_added.value
-        self._handle_failures(st == _native.PB_ERR_CUCKOO_FULL, n_failed.value, failed)
+            if st not in (_native.PB_OK, _native.PB_ERR_CUCKOO_FULL):
+                _native.check(st)
+            self._inserted += n_added.value
+            self._handle_failures(st == _native.PB_ERR_CUCKOO_FULL, n_failed.value, failed)
+            return
+        fps, alt = self._plugin_pairs(self._as_list(keys))
+        if fps.size == 0:
+            return
+        failed = self._add_pairs(fps, alt)
+        self._handle_failures(failed.size > 0, failed.size, failed)
 
     def check_many(self, keys) -> np.ndarray:
         """CuckooFilter.check (cuckoo.py:306-315) for every key -> bool[n]"""
@@ -296,14 +339,43 @@ class CuckooFilter:
             if kb.n:
                 _native.call("pb_cuckoo_check_keys", self._h, kb.ref(), C.c_void_p(out.ctypes.data), 0)
             return out.astype(bool)
-        if isinstance(keys, (str, bytes, bytearray, memoryview)):
-            keys = [keys]
-        fps = self._plugin_fingerprints(keys)
+        fps, alt = self._plugin_pairs(self._as_list(keys))
         out = np.empty(fps.size, dtype=np.uint8)
         if fps.size:
-            _native.call("pb_cuckoo_check_fingerprints", self._h, C.c_void_p(fps.ctypes.data), fps.size, 0,
-                         C.c_void_p(out.ctypes.data), 0)
+            _native.call("pb_cuckoo_check_indexed", self._h, C.c_void_p(fps.ctypes.data), C.c_void_p(alt.ctypes.data), fps.size,
+                         C.c_void_p(out.ctypes.data))
         return out.astype(bool)
+
+    def remove_many(self, keys) -> np.ndarray:
+        """CuckooFilter.remove (cuckoo.py:317-330) for every key -> bool[n] (True: a stored fingerprint was removed).
+        The table and elements_added end up as after the sequential loop.  When several keys of one batch share a
+        fingerprint exactly one of them reports True -- the first one, as in the reference, for batches of up to 2^20
+        keys (the flags are put in order on the host); beyond that it is whichever thread cleared the slot."""
+        removed = C.c_uint64(0)
+        if self._fused:
+            kb = pack_keys(keys)
+            out = np.zeros(kb.n, dtype=np.uint8)
+            if kb.n:
+                _native.call("pb_cuckoo_remove_keys", self._h, kb.ref(), C.c_void_p(out.ctypes.data), 0, C.byref(removed))
+            fps = None
+        else:
+            fps, alt = self._plugin_pairs(self._as_list(keys))
+            out = np.zeros(fps.size, dtype=np.uint8)
+            if fps.size:
+                _native.call("pb_cuckoo_remove_indexed", self._h, C.c_void_p(fps.ctypes.data), C.c_void_p(alt.ctypes.data), fps.size,
+                             C.c_void_p(out.ctypes.data), C.byref(removed))
+        self._inserted -= removed.value
+        res = out.astype(bool)
+        if 1 < res.size <= (1 << 20) and res.any():
+            if fps is None:
+                fps = self.fingerprint_info_many(keys)[2]
+            _, first = np.unique(fps, return_index=True)
+            winners = np.unique(fps[res])
+            ordered = np.zeros_like(res)
+            uniq = fps[first]
+            ordered[first[np.isin(uniq, winners)]] = True
+            res = ordered
+        return res
 
     def add(self, key) -> None:
         self.add_many([key])
@@ -311,8 +383,15 @@ class CuckooFilter:
     def check(self, key) -> bool:
         return bool(self.check_many([key])[0])
 
+    def remove(self, key) -> bool:
+        """cuckoo.py:317-330"""
+        return bool(self.remove_many([key])[0])
+
     def fingerprint_info_many(self, keys):
         """_generate_fingerprint_info (cuckoo.py:492-506) for a batch -> (idx_1, idx_2, fingerprint) arrays"""
+        if not self._fused:
+            fps, alt = self._plugin_pairs(self._as_list(keys))
+            return (fps.astype(np.uint64) % np.uint64(self._capacity)), alt, fps
         kb = pack_keys(keys)
         fp = np.empty(kb.n, dtype=np.uint32)
         i1 = np.empty(kb.n, dtype=np.uint64)
@@ -329,6 +408,19 @@ class CuckooFilter:
     # ------------------------------------------------------------------ expansion (cuckoo.py:351-353, :455-481)
     def _expand_device(self) -> None:
         new_cap = self._capacity * self._expansion_rate
+        if not self._fused:
+            # cuckoo.py:455-481 with the user's hash: collect, re-create at the new capacity, re-insert in bucket order
+            slots, has_zero = self.slots_numpy()
+            fps = slots.reshape(-1)
+            fps = fps[fps != 0]
+            if has_zero:
+                fps = np.concatenate([np.zeros(1, dtype=np.uint32), fps])
+            _native.call("pb_cuckoo_resize", self._h, new_cap)
+            self._capacity = new_cap
+            self._inserted = 0
+            if fps.size and self._add_pairs(np.ascontiguousarray(fps), self._plugin_alt(fps)).size:
+                raise CuckooFilterFullError("The CuckooFilter failed to expand")
+            return
         n_failed = C.c_uint64(0)
         failed = np.zeros(_FAILED_CAP, dtype=np.uint32)
         st = _native.lib().pb_cuckoo_expand(self._h, new_cap, C.byref(n_failed), C.c_void_p(failed.ctypes.data), failed.size)
@@ -363,22 +455,24 @@ class CuckooFilter:
         slots = np.frombuffer(data[: self._capacity * self._bucket_size * 4], dtype=np.uint32)
         _native.call("pb_cuckoo_upload", self._h, C.c_void_p(slots.ctypes.data), slots.size, 0)
         self._inserted = int(np.count_nonzero(slots))  # zero entries are dropped on load (cuckoo.py:429)
+        self._upload_alt(slots)
+
+    def _upload_alt(self, flat_slots: np.ndarray) -> None:
+        """pre-indexed filters: the idx_2 of every stored fingerprint, from the user's hash function"""
+        if self._fused:
+            return
+        alt = np.zeros(flat_slots.size, dtype=np.uint64)
+        nz = np.nonzero(flat_slots)[0]
+        if nz.size:
+            alt[nz] = self._plugin_alt(flat_slots[nz])
+        _native.call("pb_cuckoo_set_alt", self._h, C.c_void_p(alt.ctypes.data), alt.size)
 
     # ------------------------------------------------------------------ sizing helpers (cuckoo.py:433-438, :518-524)
     def _set_error_rate(self, error_rate) -> None:
         if error_rate is not None:
             self._error_rate = error_rate
             bits = int(math.ceil(math.log2(1.0 / self._error_rate) + math.log2(self._bucket_size) + 1))
-            if bits != self._fingerprint_bits:
-                self._fingerprint_bits = bits
-                if self._inserted == 0:
-                    self._create()
-                else:
-                    # a loaded filter keeps its table; only the mask applied to new keys changes
-                    slots, z = self.slots_numpy()
-                    self._create()
-                    flat = np.ascontiguousarray(slots.reshape(-1))
-                    _native.call("pb_cuckoo_upload", self._h, C.c_void_p(flat.ctypes.data), flat.size, int(z))
+            self._set_fingerprint_bits(bits)
 
     def _calc_error_rate(self) -> float:
         return float(1 / (2 ** (self._fingerprint_bits - (math.log2(self._bucket_size) + 1))))

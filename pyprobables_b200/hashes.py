@@ -41,13 +41,22 @@ def default_fnv_1a(key: KeyT, depth: int = 1) -> list:
     return [int(x) for x in hash_many([key], depth)[0]]
 
 
+def _hash_from(key: KeyT, start: int, bits: int, device: int = 0) -> int:
+    kb = pack_keys([key])
+    out = np.empty(1, dtype=np.uint64)
+    ctx = _native.default_context(device)
+    _native.call("pb_hash_keys_from", ctx.handle, kb.ref(), start & 0xFFFFFFFFFFFFFFFF, bits, C.c_void_p(out.ctypes.data), 0)
+    return int(out[0])
+
+
 def fnv_1a(key: KeyT, seed: int = 0) -> int:
-    """64-bit FNV-1a started from basis + 31*seed (hashes.py:86-103)"""
-    seed = int(seed)
-    if not 0 <= seed < 64:
-        # the device entry point evaluates seeds 0..depth-1 (what default_fnv_1a and the filters use)
-        raise ValueError("fnv_1a: seed must be in 0..63")
-    return int(hash_many([key], seed + 1)[0, seed])
+    """64-bit FNV-1a started from basis + 31*seed, any integer seed (hashes.py:86-103)"""
+    return _hash_from(key, (14695981039346656037 + 31 * int(seed)) & 0xFFFFFFFFFFFFFFFF, 64)
+
+
+def fnv_1a_32(key: KeyT, seed: int = 0) -> int:
+    """32-bit FNV-1a started from 0x811C9DC5 + 31*seed (hashes.py:106-122)"""
+    return _hash_from(key, (0x811C9DC5 + 31 * int(seed)) & 0xFFFFFFFF, 32)
 
 
 def hash_with_depth_bytes(func):

@@ -9,12 +9,12 @@ parallel.  add_many per chunk of local keys:
     exchange all-to-all-v of the u64 indices over NVLink                      (NCCL send/recv group)
     apply    RED.OR of the received indices into the local shard            (one CUDA kernel)
 The concatenation of the shards is bit-identical to the single-GPU (and the reference's) bit array.
-check_many all-gathers the probe keys, lets every rank AND the bits it owns (bits of other shards are
-neutral) and all-reduces the partial answers with MIN.
+check_many sends the k bit indices of every probe key to the owners of those bits, gets one byte per index
+back and ANDs them at the source.
 
 Count-Min: addition commutes, so every rank keeps a private full table for its share of the stream
-and merge() sums them with one all-reduce -- the reference's join() (countminsketch.py:356-399) across
-ranks.
+and merge() sums them with one all-reduce into a separate merged table -- the reference's join()
+(countminsketch.py:356-399) across ranks.
 """
 
 from __future__ import annotations
@@ -103,6 +103,10 @@ def exchange_indices(send_segments, recv_counts, group=None):
     assert len(send_segments) == world
     recv_counts = [int(x) for x in recv_counts]
     proto = send_segments[0]
+    if dist.get_backend(group) == "gloo" and proto.is_cuda:
+        # gloo moves host memory only (CPU tests; several ranks sharing one GPU): stage through the host
+        recv, offs = exchange_indices([s.cpu() for s in send_segments], recv_counts, group)
+        return recv.to(proto.device), offs
     recv = torch.empty(sum(recv_counts), dtype=proto.dtype, device=proto.device)
     offs = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
     outs = [recv[offs[r] : offs[r + 1]] for r in range(world)]
@@ -146,13 +150,52 @@ def device_view(ptr: int, n: int, typestr: str, device: int):
     return torch.as_tensor(_DevView(ptr, n, typestr), device=f"cuda:{device}")
 
 
+def _ctl_device(group, device: int):
+    """where control-plane tensors live: on the GPU for NCCL, on the host for gloo (CPU tests, and several ranks
+    sharing one GPU where NCCL refuses to run)"""
+    import torch
+    import torch.distributed as dist
+
+    return torch.device(f"cuda:{device}") if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def _all_gather_rows(t, group):
+    """all-gather of equally shaped device tensors -> list per rank (staged through the host under gloo)"""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "gloo" and t.is_cuda:
+        host = t.cpu()
+        outs = [torch.empty_like(host) for _ in range(world)]
+        dist.all_gather(outs, host, group=group)
+        return [o.to(t.device) for o in outs]
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return outs
+
+
+def _all_reduce_int(value: int, op, group, device: int) -> int:
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_ctl_device(group, device))
+    dist.all_reduce(t, op=op, group=group)
+    return int(t.item())
+
+
 class ShardedBloomFilter:
     """One logical BloomFilter(est_elements, false_positive_rate) range-sharded over the ranks of `group`.
     Every rank constructs it with the same arguments; `add_many` takes each rank's own keys (device
-    resident uint8[n,16] tensors or anything pack_keys accepts)."""
+    resident uint8[n,16] tensors or anything pack_keys accepts).
 
-    def __init__(self, est_elements, false_positive_rate, group=None, device=None, context=None, chunk_keys: int = 1 << 26,
-                 mode: str = "fused"):
+    mode "p2p" (default): partition + exchange over NVLink peer memory + apply (csrc/pb_p2p.cu); the data path uses no
+    NCCL.  mode "route": u64 bit indices binned by owner, NCCL all-to-all-v, RED apply -- exact for any key
+    distribution, also the fallback for indices that overflow a p2p sublist.  mode "gather": all-gather the keys,
+    every rank hashes everything and applies its own range (any key width)."""
+
+    def __init__(self, est_elements, false_positive_rate, group=None, device=None, context=None, chunk_keys: int = 1 << 27,
+                 mode: str = "p2p"):
         import torch
         import torch.distributed as dist
 
@@ -170,8 +213,10 @@ class ShardedBloomFilter:
         # run on torch's current stream so kernels, NCCL collectives and tensor ops are ordered without
         # host synchronization (handle 0 is the legacy default stream = cudaStreamLegacy, 0x1)
         self._ctx = context if context is not None else torch_stream_context(self.device)
-        if mode not in ("p2p", "p2p_direct", "fused", "route", "gather"):
-            raise ValueError("mode must be 'p2p', 'p2p_direct', 'fused', 'route' or 'gather'")
+        if mode not in ("p2p", "route", "gather"):
+            raise ValueError("mode must be 'p2p', 'route' or 'gather'")
+        if mode == "p2p" and self._k > 16:
+            mode = "route"  # the partition kernels are instantiated for up to 16 hashes
         self.mode = mode
         self.chunk_keys = int(chunk_keys)
         h = C.c_void_p()
@@ -181,8 +226,7 @@ class ShardedBloomFilter:
         self._els_added = 0
         self._send = None
         self._counts = None
-        self._fused_bufs = None
-        self._s_part = self._s_comm = self._ctx_part = None
+        self._s_part = self._ctx_part = None
         self._p2p = None
 
     # -- properties in the reference's vocabulary
@@ -241,6 +285,14 @@ class ShardedBloomFilter:
         _native.call("pb_bloom_popcount", self._h, C.byref(n))
         return n.value
 
+    def test_bit_indices(self, idx):
+        """for global bit indices (int64 CUDA tensor) inside this shard's range: uint8 tensor of the bits"""
+        torch = self._torch
+        out = torch.zeros(idx.numel(), dtype=torch.uint8, device=idx.device)
+        if idx.numel() and self._h is not None:
+            _native.call("pb_bloom_test_bit_indices", self._h, C.c_void_p(idx.data_ptr()), idx.numel(), C.c_void_p(out.data_ptr()))
+        return out
+
     # -- hot path
     def _ensure_buffers(self, chunk: int, worst_case: bool = False):
         torch = self._torch
@@ -264,143 +316,53 @@ class ShardedBloomFilter:
             return torch.from_numpy(np.ascontiguousarray(keys)).to(f"cuda:{self.device}")
         raise TypeError("sharded filters take fixed-width uint8[n, L] key arrays (numpy or torch)")
 
+    def _n_chunks(self, n: int, chunk: int) -> int:
+        """all ranks walk the same number of chunks"""
+        return _all_reduce_int(-(-n // chunk), self._dist.ReduceOp.MAX, self.group, self.device)
+
     def add_many(self, keys) -> None:
         """BloomFilter.add (bloom.py:234-250) for this rank's keys; collective: every rank must call it
         (an empty batch is fine)"""
-        torch, dist = self._torch, self._dist
         t = self._device_keys(keys)
         n = int(t.shape[0])
         if self.mode == "gather":
             self._add_gather(t)
-            self._els_added += n
-            return
-        if t.shape[1] != 16:
-            raise TypeError("fused/route modes take 16-byte keys; use mode='gather' for other widths")
-        if self.mode == "fused":
-            self._add_fused(t)
-            self._els_added += n
-            return
-        if self.mode in ("p2p", "p2p_direct"):
+        elif t.shape[1] != 16:
+            raise TypeError("p2p/route modes take 16-byte keys; use mode='gather' for other widths")
+        elif self.mode == "p2p":
             self._add_p2p(t)
-            self._els_added += n
-            return
-        self._add_route(t, self.chunk_keys, worst_case=False)
+        else:
+            self._add_route(t, min(self.chunk_keys, 1 << 26))
         self._els_added += n
 
-    def _add_route(self, t, chunk_keys: int, worst_case: bool) -> None:
-        """u64 global indices binned by owner + all-to-all-v with counts + RED apply.  worst_case sizes every
-        owner's slot for ALL indices of a chunk, which makes the path exact for any key distribution."""
+    def _add_route(self, t, chunk_keys: int) -> None:
+        """u64 global indices binned by owner + all-to-all-v with counts + RED apply.  Slots are sized for a uniform
+        spread; a chunk whose keys are too skewed for them is redone with worst-case slots -- the decision is
+        collective (all-reduce of the overflow flag), so no rank is ever left alone inside a collective."""
         torch, dist = self._torch, self._dist
         n = int(t.shape[0])
-        n_chunks = torch.tensor([-(-n // chunk_keys)], dtype=torch.int64, device=t.device)
-        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)  # all ranks walk the same number of chunks
-        for ci in range(int(n_chunks.item())):
+        for ci in range(self._n_chunks(n, chunk_keys)):
             lo = min(ci * chunk_keys, n)
             hi = min(lo + chunk_keys, n)
-            self._ensure_buffers(max(hi - lo, 1), worst_case)
-            self._counts.zero_()
-            if hi > lo:
-                kb = pack_keys(t[lo:hi], sync=False)
-                _native.call("pb_bloom_route_keys", self._ctx.handle, kb.ref(), self._m, self._k, self.plan.shard_bits,
-                             self.world, C.c_void_p(self._send.data_ptr()), self._slot, C.c_void_p(self._counts.data_ptr()))
-            counts = self._counts[: self.world].clone()
-            if int(counts.max().item()) > self._slot:
-                raise RuntimeError("routing slot overflow: keys are too skewed for the slot size; lower chunk_keys")
-            recv_counts = exchange_counts(counts, self.group)
+            for worst_case in (False, True):
+                self._ensure_buffers(max(hi - lo, 1), worst_case)
+                self._counts.zero_()
+                if hi > lo:
+                    kb = pack_keys(t[lo:hi], sync=False)
+                    _native.call("pb_bloom_route_keys", self._ctx.handle, kb.ref(), self._m, self._k, self.plan.shard_bits,
+                                 self.world, C.c_void_p(self._send.data_ptr()), self._slot, C.c_void_p(self._counts.data_ptr()))
+                counts = self._counts[: self.world].clone()
+                over = _all_reduce_int(int(counts.max().item()) > self._slot, dist.ReduceOp.MAX, self.group, self.device)
+                if not over:
+                    break
+            recv_counts = exchange_counts(counts.to(_ctl_device(self.group, self.device)), self.group)
             c_host = counts.tolist()
             segs = [self._send[d * self._slot : d * self._slot + c_host[d]] for d in range(self.world)]
             recv, _ = exchange_indices(segs, recv_counts.tolist(), self.group)
             if recv.numel() and self._h is not None:
                 _native.call("pb_bloom_add_bit_indices", self._h, C.c_void_p(recv.data_ptr()), recv.numel())
 
-    # -- fused route + partition (default): see pb_bloom_partition_keys in include/pb200.h
-    def _fused_buffers(self, chunk: int):
-        torch = self._torch
-        plan = self.plan
-        if self._fused_bufs is not None and self._fused_bufs["chunk"] >= chunk:
-            return self._fused_bufs
-        W = plan.total_windows
-        slack = C.c_uint64()
-        _native.call("pb_bloom_partition_slack", self._ctx.handle, chunk, self._k, W, C.byref(slack))
-        expect = chunk * self._k * (1 << plan.window_log2) / self._m
-        cap = int(expect * 1.03 + 6.0 * math.sqrt(expect + 1.0)) + slack.value
-        cap = (cap + 3) // 4 * 4
-        if cap * W > 0xFFFFFFF0:
-            raise ValueError("chunk_keys too large for the staging layout; lower chunk_keys")
-        dev = f"cuda:{self.device}"
-        i32 = torch.int32
-        b = {"chunk": chunk, "cap": cap,
-             # two halves of everything: pass 1 of chunk c+1, the all-to-all of chunk c and pass 2 of chunk c-1 overlap
-             "send": [torch.empty(W * cap, dtype=i32, device=dev) for _ in range(2)],
-             "recv": [torch.empty(W * cap, dtype=i32, device=dev) for _ in range(2)],
-             "scur": [torch.zeros(W, dtype=i32, device=dev) for _ in range(2)],
-             "rcur": [torch.zeros(W, dtype=i32, device=dev) for _ in range(2)],
-             "ovf": torch.empty(1 << 22, dtype=torch.int64, device=dev), "ovf_n": torch.zeros(1, dtype=torch.int64, device=dev),
-             "ev_part": [torch.cuda.Event() for _ in range(2)], "ev_comm": [torch.cuda.Event() for _ in range(2)],
-             "ev_apply": [torch.cuda.Event() for _ in range(2)]}
-        if self._s_part is None:
-            self._s_part = torch.cuda.Stream(device=self.device)
-            self._s_comm = torch.cuda.Stream(device=self.device)
-            self._ctx_part = _native.Context(self.device, stream=self._s_part.cuda_stream)
-        self._fused_bufs = b
-        return b
-
-    def _add_fused(self, t) -> None:
-        """three-stage pipeline over chunks of keys, one CUDA stream per stage:
-             pass 1 (hash + bin by global window)  ->  NCCL all-to-all of the window lists  ->  pass 2 (RED.OR into my shard)
-        Pass 2 runs on the stream the filter was created on, so everything the caller does next is ordered after it."""
-        torch, dist = self._torch, self._dist
-        plan = self.plan
-        n = int(t.shape[0])
-        n_chunks = torch.tensor([-(-n // self.chunk_keys)], dtype=torch.int64, device=t.device)
-        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)
-        n_chunks = int(n_chunks.item())
-        if n_chunks == 0:
-            return
-        b = self._fused_buffers(min(self.chunk_keys, max(n, 1)) if n_chunks == 1 else self.chunk_keys)
-        main = torch.cuda.current_stream(self.device)
-        b["ovf_n"].zero_()
-        self._s_part.wait_stream(main)  # keys and the zeroed overflow counter are ready
-        self._s_comm.wait_stream(main)
-        act = plan.active_windows(self.rank)
-        for ci in range(n_chunks):
-            h = ci & 1
-            lo = min(ci * self.chunk_keys, n)
-            hi = min(lo + self.chunk_keys, n)
-            kb = pack_keys(t[lo:hi], sync=False) if hi > lo else pack_keys(t[:0], sync=False)
-            with torch.cuda.stream(self._s_part):
-                if ci >= 2:
-                    self._s_part.wait_event(b["ev_comm"][h])  # the all-to-all that read this send half is done
-                _native.call("pb_bloom_partition_keys", self._ctx_part.handle, kb.ref(), self._m, self._k, plan.window_log2,
-                             plan.total_windows, b["cap"], C.c_void_p(b["send"][h].data_ptr()), C.c_void_p(b["scur"][h].data_ptr()),
-                             C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
-                b["ev_part"][h].record(self._s_part)
-            with torch.cuda.stream(self._s_comm):
-                self._s_comm.wait_event(b["ev_part"][h])
-                if ci >= 2:
-                    self._s_comm.wait_event(b["ev_apply"][h])  # pass 2 that read this receive half is done
-                dist.all_to_all_single(b["rcur"][h], b["scur"][h], group=self.group)
-                dist.all_to_all_single(b["recv"][h], b["send"][h], group=self.group)
-                b["ev_comm"][h].record(self._s_comm)
-            main.wait_event(b["ev_comm"][h])
-            if self._h is not None and act > 0:
-                _native.call("pb_bloom_apply_window_lists", self._h, C.c_void_p(b["recv"][h].data_ptr()),
-                             C.c_void_p(b["rcur"][h].data_ptr()), self.world, plan.windows_per_rank, act, b["cap"], plan.window_log2)
-            b["ev_apply"][h].record(main)
-        main.wait_stream(self._s_part)
-        main.wait_stream(self._s_comm)
-        # indices that did not fit their window list (heavily duplicated keys): exact slow path, all ranks together
-        worst = b["ovf_n"].clone()
-        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
-        worst = int(worst.item())
-        if worst > b["ovf"].numel():
-            # more strays than the list holds (e.g. one key repeated millions of times): OR is idempotent, so
-            # simply run the whole batch again through the exact u64 route with worst-case slots
-            self._add_route(t, min(self.chunk_keys, 1 << 20), worst_case=True)
-        elif worst > 0:
-            self._route_indices(b["ovf"][: int(b["ovf_n"].item())])
-
-    # -- fused compute + exchange over NVLink peer memory: see pb_p2p_* in include/pb200.h
+    # -- partition + exchange over NVLink peer memory: see pb_p2p_* in include/pb200.h
     def _p2p_setup(self, chunk: int):
         torch, dist = self._torch, self._dist
         if self._p2p is not None and self._p2p["chunk"] >= chunk:
@@ -411,36 +373,32 @@ class ShardedBloomFilter:
         W = plan.total_windows
         if self._s_part is None:
             self._s_part = torch.cuda.Stream(device=self.device)
-            self._s_comm = torch.cuda.Stream(device=self.device)
             self._ctx_part = _native.Context(self.device, stream=self._s_part.cuda_stream)
-        slack = C.c_uint64()
-        _native.call("pb_bloom_partition_slack", self._ctx.handle, chunk, self._k, W, C.byref(slack))
-        expect = chunk * self._k * (1 << plan.window_log2) / self._m
-        cap = int(expect * 1.03 + 6.0 * math.sqrt(expect + 1.0)) + slack.value
-        cap = (cap + 3) // 4 * 4
+        n_sub, sub_cap = C.c_uint32(), C.c_uint32()
+        _native.call("pb_bloom_partition_layout", self._ctx_part.handle, chunk, self._k, self._m, plan.window_log2, W,
+                     C.byref(n_sub), C.byref(sub_cap))
         h = C.c_void_p()
-        _native.call("pb_p2p_create", self._ctx_part.handle, self.world, self.rank, plan.windows_per_rank, cap, C.byref(h))
-        _native.call("pb_p2p_set_direct", h, 1 if self.mode == "p2p_direct" else 0)
+        _native.call("pb_p2p_create", self._ctx_part.handle, self.world, self.rank, plan.windows_per_rank, n_sub.value, sub_cap.value,
+                     C.byref(h))
         dev = f"cuda:{self.device}"
         mine = np.zeros(64, dtype=np.uint8)
         _native.call("pb_p2p_export", h, C.c_void_p(mine.ctypes.data))
-        allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allh, torch.from_numpy(mine).to(dev), group=self.group)
-        handles = np.ascontiguousarray(allh.cpu().numpy())
+        ctl = _ctl_device(self.group, self.device)
+        allh = [torch.empty(64, dtype=torch.uint8, device=ctl) for _ in range(self.world)]
+        dist.all_gather(allh, torch.from_numpy(mine).to(ctl), group=self.group)
+        handles = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
         _native.call("pb_p2p_connect", h, C.c_void_p(handles.ctypes.data))
         dist.barrier(group=self.group)  # every mailbox is mapped everywhere before anyone writes
-        self._p2p = {"chunk": chunk, "cap": cap, "h": h,
+        self._p2p = {"chunk": chunk, "h": h, "n_sub": n_sub.value, "sub_cap": sub_cap.value,
                      "ovf": torch.empty(1 << 22, dtype=torch.int64, device=dev), "ovf_n": torch.zeros(1, dtype=torch.int64, device=dev)}
         return self._p2p
 
     def _add_p2p(self, t) -> None:
-        """pass 1 stores into the owners' mailboxes over NVLink (stream s_part); pass 2 on the filter's stream"""
+        """pass 1 + copy-engine pushes on stream s_part; pass 2 on the filter's stream"""
         torch, dist = self._torch, self._dist
         plan = self.plan
         n = int(t.shape[0])
-        n_chunks = torch.tensor([-(-n // self.chunk_keys)], dtype=torch.int64, device=t.device)
-        dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX, group=self.group)
-        n_chunks = int(n_chunks.item())
+        n_chunks = self._n_chunks(n, self.chunk_keys)
         if n_chunks == 0:
             return
         b = self._p2p_setup(self.chunk_keys)
@@ -456,78 +414,127 @@ class ShardedBloomFilter:
                          C.c_void_p(b["ovf"].data_ptr()), b["ovf"].numel(), C.c_void_p(b["ovf_n"].data_ptr()))
             _native.call("pb_p2p_apply", b["h"], self._h, act, plan.window_log2)
         main.wait_stream(self._s_part)  # (the last pass 2 on `main` already waited for every source's copies)
-        worst = b["ovf_n"].clone()
-        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
-        worst = int(worst.item())
+        # one control-plane exchange per batch: did anybody's flag wait time out, did any sublist overflow?
+        mine_ovf = int(b["ovf_n"].item())  # synchronizes `main`
+        aborted = C.c_int(0)
+        _native.call("pb_p2p_check", b["h"], C.byref(aborted))
+        if _all_reduce_int(aborted.value, dist.ReduceOp.MAX, self.group, self.device):
+            raise RuntimeError("multi-GPU insert aborted: a rank stopped answering (flag wait timed out, p2p_timeout_ms)")
+        worst = _all_reduce_int(mine_ovf, dist.ReduceOp.MAX, self.group, self.device)
         if worst > b["ovf"].numel():
-            self._add_route(t, min(self.chunk_keys, 1 << 20), worst_case=True)
+            # more strays than the list holds (e.g. one key repeated millions of times): OR is idempotent, so
+            # simply run the whole batch again through the exact u64 route
+            self._add_route(t, min(self.chunk_keys, 1 << 20))
         elif worst > 0:
-            self._route_indices(b["ovf"][: int(b["ovf_n"].item())])
+            self._route_indices(b["ovf"][:mine_ovf])
 
     def _route_indices(self, idx) -> None:
         """send global bit indices (int64 tensor) to their owners and OR them in (collective)"""
-        torch = self._torch
-        owner = torch.div(idx, self.plan.shard_bits, rounding_mode="floor")
-        order = torch.argsort(owner)
-        idx = idx[order].contiguous()
-        counts = torch.bincount(owner, minlength=self.world)[: self.world]
-        recv_counts = exchange_counts(counts, self.group)
-        offs = [0] + torch.cumsum(counts, 0).tolist()
-        segs = [idx[offs[d] : offs[d + 1]] for d in range(self.world)]
-        recv, _ = exchange_indices(segs, recv_counts.tolist(), self.group)
+        recv, _, _ = self._exchange_by_owner(idx)
         if recv.numel() and self._h is not None:
             _native.call("pb_bloom_add_bit_indices", self._h, C.c_void_p(recv.data_ptr()), recv.numel())
 
+    def _exchange_by_owner(self, idx):
+        """all-to-all-v of global bit indices to the ranks that own them.  Returns (what I received, the order my
+        indices were sent in, how many went to each rank) -- the last two let answers travel back."""
+        torch = self._torch
+        owner = torch.div(idx, self.plan.shard_bits, rounding_mode="floor")
+        order = torch.argsort(owner, stable=True)
+        sent = idx[order].contiguous()
+        counts = torch.bincount(owner, minlength=self.world)[: self.world]
+        recv_counts = exchange_counts(counts.to(_ctl_device(self.group, self.device)), self.group)
+        offs = [0] + torch.cumsum(counts, 0).tolist()
+        segs = [sent[offs[d] : offs[d + 1]] for d in range(self.world)]
+        recv, _ = exchange_indices(segs, recv_counts.tolist(), self.group)
+        return recv, order, (counts.tolist(), recv_counts.tolist())
+
     def _add_gather(self, t) -> None:
         torch, dist = self._torch, self._dist
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        sizes = [torch.empty_like(n) for _ in range(self.world)]
-        dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        sizes = self._all_sizes(int(t.shape[0]))
         mx = max(sizes)
         if mx == 0:
             return
         pad = torch.zeros((mx, t.shape[1]), dtype=torch.uint8, device=t.device)
         pad[: t.shape[0]] = t
-        allk = torch.empty((self.world, mx, t.shape[1]), dtype=torch.uint8, device=t.device)
-        dist.all_gather_into_tensor(allk, pad, group=self.group)
+        allk = _all_gather_rows(pad, self.group)
         if self._h is None:
             return
         for r in range(self.world):
             if sizes[r]:
-                _native.call("pb_bloom_add_keys", self._h, pack_keys(allk[r, : sizes[r]], sync=False).ref())
+                _native.call("pb_bloom_add_keys", self._h, pack_keys(allk[r][: sizes[r]], sync=False).ref())
         self._ctx.synchronize()
 
-    def check_many(self, keys):
-        """BloomFilter.check for this rank's keys -> bool tensor; collective"""
+    def _all_sizes(self, n: int) -> list[int]:
+        torch, dist = self._torch, self._dist
+        mine = torch.tensor([n], dtype=torch.int64, device=_ctl_device(self.group, self.device))
+        sizes = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(sizes, mine, group=self.group)
+        return [int(s.item()) for s in sizes]
+
+    def check_many(self, keys, chunk_keys: int = 1 << 24):
+        """BloomFilter.check (bloom.py:252-272) for this rank's keys -> bool tensor; collective.
+        The k bit indices of every key travel to the ranks that own the bits (all-to-all-v, 8 B per index), the
+        owners answer with one byte per index, and the source ANDs the k answers of each key: the traffic per key does
+        not grow with the number of ranks and every key is hashed once, on its own rank.  mode 'gather' keeps the
+        simple scheme (all-gather the keys, AND of partial answers by all-reduce) for keys that are not 16 bytes."""
         torch, dist = self._torch, self._dist
         t = self._device_keys(keys)
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        sizes = [torch.empty_like(n) for _ in range(self.world)]
-        dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        if self.mode == "gather" or t.shape[1] != 16:
+            return self._check_gather(t)
+        n = int(t.shape[0])
+        out = torch.empty(n, dtype=torch.uint8, device=t.device)
+        for ci in range(self._n_chunks(n, chunk_keys)):
+            lo = min(ci * chunk_keys, n)
+            hi = min(lo + chunk_keys, n)
+            m = hi - lo
+            idx = torch.empty(m * self._k, dtype=torch.int64, device=t.device)
+            if m:
+                _native.call("pb_bloom_index_keys", self._ctx.handle, pack_keys(t[lo:hi], sync=False).ref(), self._m, self._k,
+                             C.c_void_p(idx.data_ptr()))
+            recv, order, (sent_counts, recv_counts) = self._exchange_by_owner(idx)
+            answers = self.test_bit_indices(recv)
+            a_off = [0] + np.cumsum(recv_counts).tolist()
+            back, _ = exchange_indices([answers[a_off[r] : a_off[r + 1]] for r in range(self.world)], sent_counts, self.group)
+            if m:
+                bits = torch.empty(m * self._k, dtype=torch.uint8, device=t.device)
+                bits[order] = back  # answers arrive in the order the indices were sent
+                _native.call("pb_bloom_and_rows", self._ctx.handle, C.c_void_p(bits.data_ptr()), m, self._k,
+                             C.c_void_p(out[lo:hi].data_ptr()))
+        self._ctx.synchronize()
+        return out.bool()
+
+    def _check_gather(self, t):
+        torch, dist = self._torch, self._dist
+        sizes = self._all_sizes(int(t.shape[0]))
         mx = max(sizes)
         if mx == 0:
             return torch.zeros(0, dtype=torch.bool, device=t.device)
         pad = torch.zeros((mx, t.shape[1]), dtype=torch.uint8, device=t.device)
         pad[: t.shape[0]] = t
-        allk = torch.empty((self.world, mx, t.shape[1]), dtype=torch.uint8, device=t.device)
-        dist.all_gather_into_tensor(allk, pad, group=self.group)
+        allk = _all_gather_rows(pad, self.group)
         partial = torch.ones((self.world, mx), dtype=torch.uint8, device=t.device)
         if self._h is not None:
             for r in range(self.world):
                 if sizes[r]:
-                    _native.call("pb_bloom_check_keys", self._h, pack_keys(allk[r, : sizes[r]], sync=False).ref(),
+                    _native.call("pb_bloom_check_keys", self._h, pack_keys(allk[r][: sizes[r]], sync=False).ref(),
                                  C.c_void_p(partial[r].data_ptr()), 1)
             self._ctx.synchronize()
-        dist.all_reduce(partial, op=dist.ReduceOp.MIN, group=self.group)
+        if dist.get_backend(self.group) == "gloo":
+            host = partial.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.MIN, group=self.group)
+            partial = host.to(t.device)
+        else:
+            dist.all_reduce(partial, op=dist.ReduceOp.MIN, group=self.group)
         return partial[self.rank, : t.shape[0]].bool()
 
 
 class ShardedCountMinSketch:
-    """data-parallel Count-Min: a private table per rank for its share of the stream; merge() gives every
-    rank the sketch of the whole stream = rank 0's table joined with rank 1..G-1's in rank order, each join
-    being the reference's CountMinSketch.join (countminsketch.py:356-399) run by the device kernel."""
+    """data-parallel Count-Min: a private table per rank for its share of the stream (`local`).  merge() builds the
+    sketch of the whole stream in a SECOND table (`merged`) that every rank holds: one all-reduce (sum) of the
+    tables widened to int64, narrowed back with the reference's saturation -- for non-negative counts exactly what
+    joining the ranks' sketches one after the other gives (CountMinSketch.join, countminsketch.py:356-399).
+    The private tables are never overwritten, so merge() can be called again after more add_many calls (periodic
+    merging) without counting anything twice."""
 
     def __init__(self, width, depth, group=None, device=None, context=None):
         import torch
@@ -543,6 +550,7 @@ class ShardedCountMinSketch:
         self.device = int(device)
         ctx = context if context is not None else torch_stream_context(self.device)
         self.local = CountMinSketch(width=width, depth=depth, device=self.device, context=ctx)
+        self.merged = CountMinSketch(width=width, depth=depth, device=self.device, context=ctx)
 
     def add_many(self, keys, num_els=1) -> None:
         self.local.add_many(keys, num_els)
@@ -551,16 +559,25 @@ class ShardedCountMinSketch:
         torch, dist = self._torch, self._dist
         c = self.local
         n = c.width * c.depth
-        mine = device_view(c.device_ptr(), n, "<i4", self.device)
-        allt = torch.empty((self.world, n), dtype=torch.int32, device=mine.device)
-        dist.all_gather_into_tensor(allt, mine, group=self.group)
-        mine.copy_(allt[0])
-        for r in range(1, self.world):
-            _native.call("pb_cms_join_buffer", c._h, C.c_void_p(allt[r].data_ptr()), n)
+        sums = torch.empty(n, dtype=torch.int64, device=f"cuda:{self.device}")
+        _native.call("pb_cms_widen", c._h, C.c_void_p(sums.data_ptr()), n)
         c._ctx.synchronize()
-        ea = torch.tensor([c.elements_added], dtype=torch.int64, device=mine.device)
-        dist.all_reduce(ea, op=dist.ReduceOp.SUM, group=self.group)
-        c._elements_added = int(ea.item())
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            host = sums.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=self.group)
+            sums.copy_(host)
+        _native.call("pb_cms_load_sums", self.merged._h, C.c_void_p(sums.data_ptr()), n)
+        c._ctx.synchronize()
+        total = _all_reduce_int(c.elements_added, dist.ReduceOp.SUM, self.group, self.device)
+        self.merged._elements_added = min(total, (1 << 63) - 1)  # countminsketch.py:285-287
+
+    @property
+    def elements_added(self) -> int:
+        """of the merged sketch (the whole stream as of the last merge())"""
+        return self.merged.elements_added
 
     def check_many(self, keys):
-        return self.local.check_many(keys)
+        """estimates from the merged sketch (call merge() first)"""
+        return self.merged.check_many(keys)

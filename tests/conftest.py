@@ -21,7 +21,9 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
-    return json.loads((ROOT / "tests" / "golden" / "golden.json").read_text())
+    g = json.loads((ROOT / "tests" / "golden" / "golden.json").read_text())
+    g.update(json.loads((ROOT / "tests" / "golden" / "golden_r2.json").read_text()))  # round-2 additions (make_golden_r2.py)
+    return g
 
 
 @pytest.fixture(scope="session")

@@ -237,3 +237,39 @@ def test_cuckoo_full(orc, golden):
     c = orc.Cuckoo(100, 2, 100, 32)
     failed = c.add(orc.pack(orc.uniform_keys(0, 400)))
     assert c.n_failed > 0 and golden["cuckoo_full"]["type"] == "CuckooFilterFullError"
+
+
+# ---------------------------------------------------------------- counting bloom (round 2 golden: make_golden_r2.py)
+def test_counting_bloom_sequences_match_reference(orc, golden):
+    """every return value and the final counters of a 399-step add / remove / check sequence recorded from the
+    reference, on a table small enough that hashes of one key collide (the double-increment quirk)"""
+    g = golden["cbloom_seq"]
+    assert g["keys_with_colliding_hashes"] > 0
+    o = orc.CountingBloom(g["num_bits"], g["k"])
+    got = []
+    for op, key, n in g["ops"]:
+        kb = orc.pack([key])
+        if op == "add":
+            got.append(int(o.add(kb, n)[0]))
+        elif op == "remove":
+            got.append(int(o.remove(kb, n)[0]))
+        else:
+            got.append(int(o.check(kb)[0]))
+    assert got == g["returns"]
+    assert o.bloom.tolist() == g["counters"] and o.elements_added == g["elements_added"]
+    gb = golden["cbloom_batch"]
+    o = orc.CountingBloom(gb["num_bits"], gb["k"])
+    o.add(orc.pack(orc.uniform_keys(0, gb["n_add"])))
+    assert hashlib.md5(o.bloom.tobytes()).hexdigest() == gb["counters_md5_after_add"]
+    o.remove(orc.pack(orc.uniform_keys(0, gb["n_remove"])))
+    assert hashlib.md5(o.bloom.tobytes()).hexdigest() == gb["counters_md5"] and o.elements_added == gb["elements_added"]
+    gc = golden["cbloom_clamped"]
+    from pyprobables_b200.bloom import optimized_params
+
+    _, k, m = optimized_params(gc["est"], gc["fpr"])
+    o = orc.CountingBloom(m, k)
+    o.add(orc.pack(orc.uniform_keys(0, 500)))
+    rets = o.remove(orc.pack(np.concatenate([orc.uniform_keys(0, 500)] * 3)), 2)
+    assert rets[:20].tolist() == gc["returns_head"]
+    assert hashlib.md5(struct.pack("<1500Q", *[int(x) for x in rets])).hexdigest() == gc["returns_md5"]
+    assert o.bloom.tolist() == gc["counters"] and o.elements_added == gc["elements_added"]
