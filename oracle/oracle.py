@@ -133,6 +133,11 @@ def pack(keys) -> Keys:
         a = np.ascontiguousarray(keys, dtype=np.uint8)
         assert a.ndim == 2
         return Keys(a, None, a.shape[0], a.shape[1], 1)
+    if isinstance(keys, tuple) and len(keys) == 2 and isinstance(keys[0], np.ndarray) and isinstance(keys[1], np.ndarray):
+        # (packed uint8 buffer, uint64 offsets[n+1]): variable-length byte keys already packed
+        data = np.ascontiguousarray(keys[0], dtype=np.uint8)
+        offs = np.ascontiguousarray(keys[1], dtype=np.uint64)
+        return Keys(data, offs, offs.size - 1, 0, 1)
     syms = []
     wide = False
     for k in keys:

@@ -386,7 +386,7 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     const uint64_t budget_entries = std::min<uint64_t>((uint64_t)ctx->stage_bytes / 4 / (uint64_t)halves, 0xFFFFFFF0ull);  // u32 entry numbers
     PartLayout lay;
     for (;;) {
-        lay = part_layout(ctx, chunk, b->k, b->num_bits, wl, (uint32_t)nw, fixed16);
+        lay = part_layout(ctx, chunk, b->k, b->num_bits, wl, (uint32_t)nw, fixed16, halves == 2);
         if ((uint64_t)lay.sub_cap * (uint64_t)lay.grid * nw <= budget_entries) break;
         if (chunk <= 4096) return pl;  // the staging budget cannot even hold a tiny chunk: direct path
         chunk = chunk - chunk / 4;
@@ -793,7 +793,7 @@ int pb_bloom_partition_layout(pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint64_t
                               uint32_t n_windows, uint32_t *n_sub, uint32_t *sub_cap) {
     PB_REQUIRE(ctx && n_sub && sub_cap && n_keys >= 1 && k >= 1 && k <= kMaxPartK, "bad argument (k must be 1..%u)", kMaxPartK);
     PB_REQUIRE(window_log2 >= 5 && window_log2 <= 31 && n_windows >= 1 && n_windows <= (uint32_t)kMaxWindows2, "bad window geometry");
-    const PartLayout L = part_layout(ctx, n_keys, k, num_bits, window_log2, n_windows, true);
+    const PartLayout L = part_layout(ctx, n_keys, k, num_bits, window_log2, n_windows, true, true);
     *n_sub = (uint32_t)L.grid;
     *sub_cap = L.sub_cap;
     return PB_OK;

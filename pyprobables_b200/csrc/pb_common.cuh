@@ -73,7 +73,7 @@ struct pb_ctx {
                                          // windows being updated stay L2 resident; 4 x 32 MiB at once thrashed: r1 sweep)
     int64_t bloom_part_tile = 0;         // keys per pass-1 tile: 0 auto (512 beyond 112 windows), 256, 512
     int64_t bloom_overlap = 1;           // run pass 2 of chunk i on aux_stream while pass 1 of chunk i+1 runs
-    int64_t bloom_part_ctas_per_sm = 4;  // pass 1: resident 256-thread CTAs per SM (registers allow 4 for k <= 8, 3 beyond)
+    int64_t bloom_part_ctas_per_sm = 0;  // pass 1: resident 256-thread CTAs per SM; 0 = auto (3 beside pass 2, else what registers allow)
     int64_t bloom_min_chunks = 8;        // overlapped partitioned insert: split a batch into at least this many chunks
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk

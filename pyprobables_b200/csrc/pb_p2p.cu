@@ -280,7 +280,7 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
     for (uint32_t r = 0; r < p->world; ++r) PB_REQUIRE(p->peer[r] != nullptr, "rank %u is not connected (pb_p2p_connect)", r);
     pb_ctx *ctx = p->send_ctx;
     DeviceGuard g(ctx->device);
-    const PartLayout need = part_layout(ctx, std::max<uint64_t>(keys->n, 1), k, num_bits, window_log2, W, true);
+    const PartLayout need = part_layout(ctx, std::max<uint64_t>(keys->n, 1), k, num_bits, window_log2, W, true, true);
     PB_REQUIRE(need.sub_cap <= p->sub_cap, "chunk of %llu keys needs sublists of %u entries, the mailbox has %u",
                (unsigned long long)keys->n, need.sub_cap, p->sub_cap);
     const unsigned long long seq = ++p->send_seq;
