@@ -7,6 +7,7 @@ raises, so a test or benchmark can never silently run somewhere else.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import os
 import subprocess
 import threading
@@ -254,7 +255,8 @@ class Context:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():  # at interpreter exit the CUDA context may already be gone
+                self.close()
         except Exception:
             pass
 

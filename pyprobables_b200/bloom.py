@@ -10,6 +10,7 @@ the user's own callable.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import math
 import mmap as _mmap
 import struct
@@ -119,7 +120,8 @@ class BloomFilter:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():  # at interpreter exit the CUDA context may already be gone
+                self.close()
         except Exception:
             pass
 
@@ -206,9 +208,18 @@ class BloomFilter:
             self._add_hash_rows(h, n)
 
     def check_many(self, keys) -> np.ndarray:
-        """BloomFilter.check (bloom.py:252-272) for every key -> bool[n]"""
+        """BloomFilter.check (bloom.py:252-272) for every key -> bool[n] (a CUDA tensor of keys gets a CUDA bool
+        tensor back: nothing crosses PCIe, and large batches of 16-byte keys take the partitioned query)"""
         if self._fused:
             kb = pack_keys(keys)
+            if kb.on_device:
+                import torch
+
+                res = torch.empty(kb.n, dtype=torch.uint8, device=f"cuda:{self._ctx.device}")
+                if kb.n:
+                    _native.call("pb_bloom_check_keys", self._h, kb.ref(), C.c_void_p(res.data_ptr()), 1)
+                    self._ctx.synchronize()
+                return res.bool()
             out = np.empty(kb.n, dtype=np.uint8)
             if kb.n:
                 _native.call("pb_bloom_check_keys", self._h, kb.ref(), C.c_void_p(out.ctypes.data), 0)

@@ -12,6 +12,7 @@ order-free) or no counter saturates; `add()` of a single key keeps the reference
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import math
 import mmap as _mmap
 import struct
@@ -97,7 +98,8 @@ class CountMinSketch:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():  # at interpreter exit the CUDA context may already be gone
+                self.close()
         except Exception:
             pass
 

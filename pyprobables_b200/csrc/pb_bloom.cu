@@ -250,6 +250,17 @@ __global__ void __launch_bounds__(256) and_rows_kernel(const uint8_t *__restrict
     }
 }
 
+// number of 1 bytes in a 0/1 byte vector (hit rate of a check sample)
+__global__ void __launch_bounds__(256) count_ones_kernel(const uint4 *__restrict__ v, uint64_t n16, unsigned long long *out) {
+    unsigned long long c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = v[i];
+        c += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // ---------------------------------------------------------------- multi-GPU routing
 // hash keys, find the owning shard of every bit index, append the (global) index to that shard's slot.
 template <int KG>
@@ -360,11 +371,12 @@ struct PartPlan {
 };
 
 // Decide whether (and how) a batch of n keys goes through the partitioned path.
-static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
+// query: the partitioned CHECK (two staged words per index, 16-byte device keys, k <= kMaxQueryK); mode = the
+// caller's 0 auto / 1 direct / 2 partitioned option
+static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16, int64_t mode, bool query = false) {
     PartPlan pl;
     pb_ctx *ctx = b->ctx;
-    const int64_t mode = ctx->bloom_insert_mode;
-    if (mode == 1 || b->k > kMaxPartK || n == 0) return pl;
+    if (mode == 1 || b->k > (query ? kMaxQueryK : kMaxPartK) || n == 0) return pl;
     if (b->lo_bit != 0 || b->hi_bit != b->num_bits) return pl;  // shards take routed indices instead
     const uint64_t l2 = ctx->l2_bytes ? ctx->l2_bytes : ((uint64_t)96 << 20);
     if (mode == 0) {
@@ -383,10 +395,12 @@ static PartPlan plan_partition(const pb_bloom *b, uint64_t n, bool fixed16) {
     const int halves = (ctx->bloom_overlap && n >= (1ull << 24)) ? 2 : 1;
     uint64_t chunk = n;
     if (halves == 2) chunk = std::max<uint64_t>((n + (uint64_t)ctx->bloom_min_chunks - 1) / (uint64_t)std::max<int64_t>(ctx->bloom_min_chunks, 2), 1ull << 22);
-    const uint64_t budget_entries = std::min<uint64_t>((uint64_t)ctx->stage_bytes / 4 / (uint64_t)halves, 0xFFFFFFF0ull);  // u32 entry numbers
+    const uint64_t budget_entries =
+        std::min<uint64_t>((uint64_t)ctx->stage_bytes / (query ? 8 : 4) / (uint64_t)halves, 0xFFFFFFF0ull);  // u32 entry numbers
+    if (query) chunk = std::min<uint64_t>(chunk, 0xFFFFFF00ull);  // key numbers inside a chunk are u32
     PartLayout lay;
     for (;;) {
-        lay = part_layout(ctx, chunk, b->k, b->num_bits, wl, (uint32_t)nw, fixed16, halves == 2);
+        lay = part_layout(ctx, chunk, b->k, b->num_bits, wl, (uint32_t)nw, fixed16, halves == 2, query);
         if ((uint64_t)lay.sub_cap * (uint64_t)lay.grid * nw <= budget_entries) break;
         if (chunk <= 4096) return pl;  // the staging budget cannot even hold a tiny chunk: direct path
         chunk = chunk - chunk / 4;
@@ -590,7 +604,7 @@ int pb_bloom_add_keys(pb_bloom *b, const pb_keys *keys) {
     a.b = b;
     const bool fixed16 = keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 &&
                          (keys->on_device ? ((uintptr_t)keys->data & 15u) == 0 : true);
-    a.plan = plan_partition(b, keys->n, fixed16);
+    a.plan = plan_partition(b, keys->n, fixed16, b->ctx->bloom_insert_mode);
     pb_ctx *ctx = b->ctx;
     const int st = for_each_chunk(ctx, keys, add_chunk, &a, a.plan.use ? a.plan.chunk_keys : 0);
     if (a.overlapped) {
@@ -606,16 +620,122 @@ int pb_bloom_add_keys(pb_bloom *b, const pb_keys *keys) {
     return st;
 }
 
+// Partitioned query of device-resident 16-byte keys (out on the device): per chunk, preset the answers to 1, bin
+// the bit indices with their key numbers by window (bloom_part4<IDS>), then test every window's indices while the
+// window is L2 resident (bloom_probe2) -- the same two overlapped passes as the insert, without a random DRAM access.
+static int check_partitioned(pb_bloom *b, const uint4 *keys, uint64_t n, uint8_t *out, const PartPlan &pl) {
+    pb_ctx *ctx = b->ctx;
+    const bool overlap = pl.halves == 2;
+    const size_t n_lists = (size_t)pl.n_windows * (size_t)pl.lay.grid;
+    const size_t half_entries = n_lists * pl.lay.sub_cap;
+    PB_TRY(scratch_reserve(ctx, ctx->part_stage, half_entries * 8 * (size_t)pl.halves));
+    PB_TRY(scratch_reserve(ctx, ctx->part_cursors, n_lists * 4 * (size_t)pl.halves));
+    PB_CUDA(probe_configure());
+    const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
+    uint64_t chunk_no = 0;
+    for (uint64_t c0 = 0; c0 < n; c0 += pl.chunk_keys, ++chunk_no) {
+        const uint64_t cn = std::min<uint64_t>(pl.chunk_keys, n - c0);
+        const int half = overlap ? (int)(chunk_no & 1) : 0;
+        PartDev pd;
+        pd.stage = (uint32_t *)ctx->part_stage.p + (size_t)half * 2 * half_entries;
+        pd.ids = pd.stage + half_entries;
+        pd.counts = (uint32_t *)ctx->part_cursors.p + (size_t)half * n_lists;
+        pd.words = b->words;
+        pd.out = out + c0;
+        part_set_modulus(pd, b->num_bits);
+        pd.sub_cap = pl.lay.sub_cap;
+        pd.n_sub = (uint32_t)pl.lay.grid;
+        pd.window_log2 = pl.window_log2;
+        pd.n_windows = pl.n_windows;
+        pd.k = b->k;
+        pd.ovf_list = nullptr;
+        pd.ovf_count = nullptr;
+        pd.ovf_cap = 0;
+        if (overlap && ctx->apply_pending[half]) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[half], 0));
+        PB_CUDA(cudaMemsetAsync(pd.out, 1, cn, ctx->stream));
+        DevKeys dk;
+        dk.data = (const uint8_t *)(keys + c0);
+        dk.offsets = nullptr;
+        dk.n = cn;
+        dk.stride = 16;
+        dk.sym_width = 1;
+        dk.base_symbol = 0;
+        dk.total_bytes = cn * 16;
+        launch_begin(ctx);
+        cudaError_t e = launch_part4_ids(pl.lay.block, ctx->stream, dk, pd);
+        if (e != cudaSuccess) {
+            set_error("launch of bloom_part4 (query, k=%u) failed: %s", pd.k, cudaGetErrorString(e));
+            return PB_ERR_CUDA;
+        }
+        PB_TRY(check_launch(ctx, "bloom_check_part"));
+        cudaStream_t s2 = ctx->stream;
+        if (overlap) {
+            s2 = ctx->aux_stream;
+            PB_CUDA(cudaEventRecord(ctx->ev_part[half], ctx->stream));
+            PB_CUDA(cudaStreamWaitEvent(s2, ctx->ev_part[half], 0));
+        }
+        launch_begin(ctx, s2);
+        bloom_probe2<<<pl.n_windows * cpw, 256, sizeof(ProbeSmem), s2>>>(pd, cpw);
+        PB_TRY(check_launch(ctx, "bloom_check_probe", s2));
+        if (overlap) {
+            PB_CUDA(cudaEventRecord(ctx->ev_apply[half], s2));
+            ctx->apply_pending[half] = true;
+        }
+    }
+    for (int h = 0; h < 2; ++h) {
+        if (ctx->apply_pending[h]) {
+            PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_apply[h], 0));
+            ctx->apply_pending[h] = false;
+        }
+    }
+    return PB_OK;
+}
+
 int pb_bloom_check_keys(pb_bloom *b, const pb_keys *keys, uint8_t *out, int out_on_device) {
     PB_REQUIRE(b && keys, "NULL argument");
     PB_REQUIRE(out || keys->n == 0, "out is NULL");
-    DeviceGuard g(b->ctx->device);
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(validate_keys(keys));
+    pb_keys rest = *keys;
+    uint8_t *out_rest = out;
+    const bool fixed16 = keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16 && ((uintptr_t)keys->data & 15u) == 0;
+    const int64_t mode = ctx->bloom_check_mode;
+    if (mode != 1 && keys->on_device && out_on_device && fixed16 && keys->n >= (mode == 2 ? 1u : (1u << 24))) {
+        // auto: the partitioned query pays when most probes run to the last bit (keys that ARE members); absent keys
+        // leave the direct kernel after two probes on average.  Decide on the hit rate of the first 2^20 keys.
+        bool go = true;
+        if (mode == 0) {
+            const uint64_t ns = 1u << 20;
+            pb_keys head = *keys;
+            head.n = ns;
+            CheckArgs a{b, out, nullptr};
+            PB_TRY(for_each_chunk(ctx, &head, check_chunk, &a));
+            PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+            unsigned long long *acc = (unsigned long long *)ctx->small.p + 100;
+            PB_CUDA(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+            count_ones_kernel<<<grid_for(ctx, ns / 16, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)out, ns / 16, acc);
+            PB_TRY(check_launch(ctx, "bloom_check_sample"));
+            uint64_t *h = (uint64_t *)((uint8_t *)ctx->pinned_small + 3584);
+            PB_CUDA(cudaMemcpyAsync(h, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            go = *h * 2 >= ns;
+            rest.data = (const uint8_t *)keys->data + ns * 16;
+            rest.n = keys->n - ns;
+            out_rest = out + ns;
+        }
+        if (go && rest.n) {
+            const PartPlan pl = plan_partition(b, rest.n, true, mode == 2 ? 2 : 0, true);
+            if (pl.use) return check_partitioned(b, (const uint4 *)rest.data, rest.n, out_rest, pl);
+        }
+        if (rest.n == 0) return PB_OK;
+    }
     CheckArgs a;
     a.b = b;
-    a.out_dev = out_on_device ? out : nullptr;
-    a.out_host = out_on_device ? nullptr : out;
-    PB_TRY(for_each_chunk(b->ctx, keys, check_chunk, &a));
-    if (!out_on_device) PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    a.out_dev = out_on_device ? out_rest : nullptr;
+    a.out_host = out_on_device ? nullptr : out_rest;
+    PB_TRY(for_each_chunk(ctx, &rest, check_chunk, &a));
+    if (!out_on_device) PB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }
 

@@ -24,12 +24,17 @@
 namespace pb {
 
 constexpr int kMaxWindows2 = 512;
-constexpr uint32_t kMaxPartK = 16;  // pass 1 is instantiated for 1..16 hashes (more take the direct path)
+constexpr uint32_t kMaxPartK = 16;   // pass 1 is instantiated for 1..16 hashes (more take the direct path)
+constexpr uint32_t kMaxQueryK = 15;  // ... the partitioned query for 1..15
 
 struct PartDev {
     uint32_t *stage;         // [n_windows][n_sub][sub_cap]
     uint32_t *counts;        // [n_windows][n_sub]
     uint32_t *words;         // the bitmap (overflow fallback of the single-GPU path; nullptr when routing)
+    // partitioned QUERY (bloom_part4<.., IDS = true> + bloom_probe2): every staged bit index carries the number of its
+    // key inside the chunk; a bit that is not set clears the key's answer byte
+    uint32_t *ids;           // [n_windows][n_sub][sub_cap], parallel to stage (nullptr for inserts)
+    uint8_t *out;            // answers of the chunk's keys, preset to 1
     uint64_t m;              // number of bits (modulus)
     uint64_t recip;          // floor(2^64 / m)
     uint32_t sub_cap;        // entries per sublist (multiple of 4)
@@ -110,8 +115,8 @@ struct PartLayout {
 
 // 512-key tiles once a 256-key tile would give a window fewer than ~16 entries ("bloom_part_tile": 0 auto, 256, 512);
 // they exist for 16-byte keys and k <= 8 only (shared memory of the sorted tile)
-inline bool part_big_tile(const pb_ctx *ctx, uint32_t n_windows, uint32_t k, bool fixed16) {
-    if (!fixed16 || k > 8 || ctx->bloom_part_tile == 256) return false;
+inline bool part_big_tile(const pb_ctx *ctx, uint32_t n_windows, uint32_t k, bool fixed16, bool query = false) {
+    if (!fixed16 || k > (query ? 7u : 8u) || ctx->bloom_part_tile == 256) return false;
     if (ctx->bloom_part_tile == 512) return true;
     return n_windows > 112;
 }
@@ -120,14 +125,14 @@ inline bool part_big_tile(const pb_ctx *ctx, uint32_t n_windows, uint32_t k, boo
 // overlapped: pass 2 of the previous chunk runs beside this launch -- then three pass-1 CTAs per SM instead of four, which
 // leaves registers and shared memory for three pass-2 CTAs instead of one (r2 sweep: 63.1 -> 59.6 ms per 1e9 keys).
 inline PartLayout part_layout(const pb_ctx *ctx, uint64_t n_keys, uint32_t k, uint64_t m, uint32_t window_log2, uint32_t n_windows,
-                              bool fixed16, bool overlapped) {
+                              bool fixed16, bool overlapped, bool query = false) {
     PartLayout L;
-    L.block = part_big_tile(ctx, n_windows, k, fixed16) ? 512 : 256;
+    L.block = part_big_tile(ctx, n_windows, k, fixed16, query) ? 512 : 256;
     // K <= 8: 56 registers -> four 256-thread CTAs per SM (+ one pass-2 CTA); K > 8: 72 registers -> three
     const int most = k <= 8 ? 4 : 3;
     const int64_t want = ctx->bloom_part_ctas_per_sm > 0 ? ctx->bloom_part_ctas_per_sm : (overlapped ? 3 : most);
     const int base = (int)std::max<int64_t>(1, std::min<int64_t>(want, most));
-    const int per_sm = std::max(1, base * 256 / L.block);
+    const int per_sm = L.block == 512 ? (base + 1) / 2 : base;  // 512-thread CTAs: two per SM
     const uint64_t tiles = (n_keys + L.block - 1) / L.block;
     L.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * per_sm));
     const double keys_per_cta = (double)((tiles + L.grid - 1) / L.grid) * L.block;
@@ -141,6 +146,8 @@ inline PartLayout part_layout(const pb_ctx *ctx, uint64_t n_keys, uint32_t k, ui
 // fourth generation of pass 1 (pb_bloom_part4.cu): any key layout, K = 1..16 hashes.  Launches pd.n_sub CTAs of
 // `block` threads (CTAs beyond the tiles of a short batch only write their zero counts).
 cudaError_t launch_part4(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd);
+// the same pass for a partitioned query (16-byte keys only): also stores each index's key number into pd.ids
+cudaError_t launch_part4_ids(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd);
 
 // ---- pass 2 ----------------------------------------------------------------------------------------------------
 // OR lists into a window's slice of the bitmap.  The lists are streamed through shared memory with TMA bulk copies
@@ -248,6 +255,85 @@ static __global__ void __launch_bounds__(256) bloom_apply_sources(uint32_t *__re
         if (cnt > sub_cap) cnt = sub_cap;
         apply_list_tma(words, stage + li * sub_cap, cnt, sm, g);
     }
+}
+
+// ---- pass 2 of the partitioned QUERY: test the staged bit indices while their window is L2 resident; a clear bit
+// writes 0 into its key's answer byte (the bytes were preset to 1, every writer stores 0: no atomics needed).
+// Entries and key numbers stream through shared memory with TMA bulk copies exactly like bloom_apply2's lists.
+struct ProbeSmem {
+    alignas(128) uint32_t loc[kApplyStages][kApplyTile];
+    alignas(128) uint32_t id[kApplyStages][kApplyTile];
+    alignas(8) uint64_t full[kApplyStages];
+};
+
+static __global__ void __launch_bounds__(256) bloom_probe2(PartDev p, uint32_t ctas_per_window) {
+    extern __shared__ __align__(128) uint8_t probe_smem_raw[];
+    ProbeSmem &sm = *reinterpret_cast<ProbeSmem *>(probe_smem_raw);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kApplyStages; ++i) mbar_init(&sm.full[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const uint32_t w = blockIdx.x / ctas_per_window;
+    const uint32_t c = blockIdx.x % ctas_per_window;
+    const uint32_t *__restrict__ words = p.words + ((uint64_t)w << (p.window_log2 - 5));
+    uint32_t g = 0;
+    for (uint32_t s = c; s < p.n_sub; s += ctas_per_window) {
+        const size_t li = (size_t)w * p.n_sub + s;
+        uint32_t cnt = p.counts[li];
+        if (cnt > p.sub_cap) cnt = p.sub_cap;
+        const uint32_t *list = p.stage + li * p.sub_cap;
+        const uint32_t *ids = p.ids + li * p.sub_cap;
+        const uint32_t T = (cnt + kApplyTile - 1) / kApplyTile;
+        auto issue = [&](uint32_t i) {  // thread 0 only
+            const uint32_t st = (g + i) % kApplyStages;
+            const uint32_t left = cnt - i * kApplyTile;
+            const uint32_t bytes = (left >= kApplyTile ? kApplyTile : ((left + 3u) & ~3u)) * 4u;
+            fence_proxy_async_smem();
+            mbar_expect_tx(&sm.full[st], 2 * bytes);
+            tma_bulk_g2s_evict_first(sm.loc[st], list + (size_t)i * kApplyTile, bytes, &sm.full[st]);
+            tma_bulk_g2s_evict_first(sm.id[st], ids + (size_t)i * kApplyTile, bytes, &sm.full[st]);
+        };
+        if (threadIdx.x == 0)
+            for (uint32_t i = 0; i < T && i < (uint32_t)kApplyStages; ++i) issue(i);
+        for (uint32_t i = 0; i < T; ++i) {
+            const uint32_t st = (g + i) % kApplyStages;
+            mbar_wait(&sm.full[st], ((g + i) / kApplyStages) & 1u);
+            const uint32_t n = min(kApplyTile, cnt - i * kApplyTile);
+            const uint4 *l4 = reinterpret_cast<const uint4 *>(sm.loc[st]);
+            const uint4 *i4 = reinterpret_cast<const uint4 *>(sm.id[st]);
+#pragma unroll
+            for (uint32_t q = 0; q < kApplyTile / 4 / 256; ++q) {
+                const uint32_t e = (q * 256 + threadIdx.x) * 4;
+                if (e < n) {
+                    const uint4 v = l4[q * 256 + threadIdx.x];
+                    const uint4 k = i4[q * 256 + threadIdx.x];
+                    // the four loads are issued before any of them is tested
+                    const uint32_t w0 = __ldg(words + (v.x >> 5));
+                    const uint32_t w1 = e + 1 < n ? __ldg(words + (v.y >> 5)) : 0xFFFFFFFFu;
+                    const uint32_t w2 = e + 2 < n ? __ldg(words + (v.z >> 5)) : 0xFFFFFFFFu;
+                    const uint32_t w3 = e + 3 < n ? __ldg(words + (v.w >> 5)) : 0xFFFFFFFFu;
+                    if (!((w0 >> (v.x & 31)) & 1u)) p.out[k.x] = 0;
+                    if (e + 1 < n && !((w1 >> (v.y & 31)) & 1u)) p.out[k.y] = 0;
+                    if (e + 2 < n && !((w2 >> (v.z & 31)) & 1u)) p.out[k.z] = 0;
+                    if (e + 3 < n && !((w3 >> (v.w & 31)) & 1u)) p.out[k.w] = 0;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && i + kApplyStages < T) issue(i + kApplyStages);
+        }
+        g += T;
+    }
+}
+
+static inline cudaError_t probe_configure() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(bloom_probe2, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bloom_probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem));
+    done = e == cudaSuccess;
+    return e;
 }
 
 // launchers of pass 2 (largest shared-memory carveout, see launch_part4_inst)

@@ -58,7 +58,9 @@ __device__ __forceinline__ void part4_bin(uint64_t h, const PartDev &p, uint32_t
     wr = atomicAdd(hist + w, kRankStep);
 }
 
-template <int K, int BS, class KS>
+// IDS: partitioned query -- every staged index also carries the number of its key inside the chunk (p.ids) and an
+// index that overflows its sublist is tested directly (p.out) instead of being ORed in
+template <int K, int BS, class KS, bool IDS = false>
 __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, PartDev p) {
     constexpr int NG = PartGroups<K>::NG, KG = PartGroups<K>::KG;
     constexpr uint32_t NW = BS / 32;
@@ -68,6 +70,7 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
     __shared__ uint32_t cur[kMaxWindows2];  // entries written so far to this CTA's sublist of each window
     __shared__ uint2 sorted[BS * K];  // {window-local bit index, gdelta}; slow path: {index, window}
     __shared__ uint32_t tile_flags[2];  // [0]: a list of this tile overflows -> slow path; [1]: entries in the tile
+    __shared__ uint16_t sorted_id[IDS ? BS * K : 1];  // IDS: the thread (= key of the tile) every sorted entry came from
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // staged key bytes (KeySrcStaged only)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = p.n_windows;
@@ -166,13 +169,17 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
 #pragma unroll
                 for (int s = 0; s < K; ++s) {
                     const Part4Tab t = tab[wr[s] >> 16];
-                    *reinterpret_cast<uint2 *>(sorted_b + t.run_bytes + (wr[s] & 0xFFFFu)) = make_uint2(loc[s], t.gdelta);
+                    const uint32_t off = t.run_bytes + (wr[s] & 0xFFFFu);
+                    *reinterpret_cast<uint2 *>(sorted_b + off) = make_uint2(loc[s], t.gdelta);
+                    if (IDS) sorted_id[off / kRankStep] = (uint16_t)tid;
                 }
             } else {
 #pragma unroll
                 for (int s = 0; s < K; ++s) {
                     const uint32_t w = wr[s] >> 16;
-                    *reinterpret_cast<uint2 *>(sorted_b + tab[w].run_bytes + (wr[s] & 0xFFFFu)) = make_uint2(loc[s], w);
+                    const uint32_t off = tab[w].run_bytes + (wr[s] & 0xFFFFu);
+                    *reinterpret_cast<uint2 *>(sorted_b + off) = make_uint2(loc[s], w);
+                    if (IDS) sorted_id[off / kRankStep] = (uint16_t)tid;
                 }
             }
         }
@@ -185,11 +192,13 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
                     const uint32_t e = s * BS + tid;
                     const uint2 v = sorted[e];
                     __stcs(p.stage + (v.y + e), v.x);
+                    if (IDS) __stcs(p.ids + (v.y + e), (uint32_t)(tile * BS) + sorted_id[e]);
                 }
             } else {
                 for (uint32_t e = tid; e < total; e += BS) {
                     const uint2 v = sorted[e];
                     __stcs(p.stage + (v.y + e), v.x);
+                    if (IDS) __stcs(p.ids + (v.y + e), (uint32_t)(tile * BS) + sorted_id[e]);
                 }
             }
         } else {
@@ -200,6 +209,10 @@ __global__ void __maxnreg__(K <= 8 ? 56 : 72) bloom_part4(KS src, uint64_t n, Pa
                 const uint32_t pos = t.gdelta + e - first;                        // position inside the sublist
                 if (pos < p.sub_cap) {
                     __stcs(p.stage + (size_t)first + pos, v.x);
+                    if (IDS) __stcs(p.ids + (size_t)first + pos, (uint32_t)(tile * BS) + sorted_id[e]);
+                } else if (IDS) {  // query: test the bit right here
+                    const uint64_t idx = ((uint64_t)v.y << p.window_log2) | v.x;
+                    if (!((p.words[idx >> 5] >> (uint32_t)(idx & 31)) & 1u)) p.out[(uint32_t)(tile * BS) + sorted_id[e]] = 0;
                 } else {
                     part_overflow(p, ((uint64_t)v.y << p.window_log2) | v.x);
                 }
@@ -226,15 +239,15 @@ static cudaError_t prefer_max_smem(Kern kern, size_t dyn) {
     return e;
 }
 
-template <int K, int BS, class KS>
+template <int K, int BS, class KS, bool IDS = false>
 static cudaError_t launch_part4_inst(const KS &src, size_t dyn, cudaStream_t stream, uint64_t n, const PartDev &pd) {
     static bool configured = false;  // per template instance
     if (!configured) {
-        cudaError_t e = prefer_max_smem(bloom_part4<K, BS, KS>, dyn);
+        cudaError_t e = prefer_max_smem(bloom_part4<K, BS, KS, IDS>, dyn);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    bloom_part4<K, BS, KS><<<(int)pd.n_sub, BS, dyn, stream>>>(src, n, pd);
+    bloom_part4<K, BS, KS, IDS><<<(int)pd.n_sub, BS, dyn, stream>>>(src, n, pd);
     return cudaSuccess;
 }
 
@@ -255,6 +268,31 @@ static cudaError_t launch_part4_k(int block, cudaStream_t stream, const DevKeys 
     const size_t dyn = kPart4StageBytes + 16;
     if (dk.sym_width == 4) return launch_part4_inst<K, 256>(KeySrcStaged<4>{dk}, dyn, stream, dk.n, pd);
     return launch_part4_inst<K, 256>(KeySrcStaged<1>{dk}, dyn, stream, dk.n, pd);
+}
+
+template <int K>
+static cudaError_t launch_part4_ids_k(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd) {
+    // the key-number array of the sorted tile costs 2 bytes per entry of shared memory: 512-key tiles up to K = 7 and
+    // 256-key tiles up to K = 15 stay inside the 48 KB of static shared memory (kMaxQueryK)
+    if (!is_fixed16(dk) || dk.n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    KeySrcFixed16 src{(const uint4 *)dk.data};
+    if constexpr (K <= 7) {
+        if (block == 512) return launch_part4_inst<K, 512, KeySrcFixed16, true>(src, 0, stream, dk.n, pd);
+    }
+    if constexpr (K <= (int)kMaxQueryK) {
+        if (block == 256) return launch_part4_inst<K, 256, KeySrcFixed16, true>(src, 0, stream, dk.n, pd);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_part4_ids(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd) {
+    switch (pd.k) {
+#define PB_P4(KK) case KK: return launch_part4_ids_k<KK>(block, stream, dk, pd);
+        PB_P4(1) PB_P4(2) PB_P4(3) PB_P4(4) PB_P4(5) PB_P4(6) PB_P4(7) PB_P4(8)
+        PB_P4(9) PB_P4(10) PB_P4(11) PB_P4(12) PB_P4(13) PB_P4(14) PB_P4(15) PB_P4(16)
+#undef PB_P4
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_part4(int block, cudaStream_t stream, const DevKeys &dk, const PartDev &pd) {

@@ -74,6 +74,7 @@ struct pb_ctx {
     int64_t bloom_part_tile = 0;         // keys per pass-1 tile: 0 auto (512 beyond 112 windows), 256, 512
     int64_t bloom_overlap = 1;           // run pass 2 of chunk i on aux_stream while pass 1 of chunk i+1 runs
     int64_t bloom_part_ctas_per_sm = 0;  // pass 1: resident 256-thread CTAs per SM; 0 = auto (3 beside pass 2, else what registers allow)
+    int64_t bloom_check_mode = 0;        // query of device keys: 0 auto (partitioned when most sampled keys are members), 1 direct, 2 partitioned
     int64_t bloom_min_chunks = 8;        // overlapped partitioned insert: split a batch into at least this many chunks
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
@@ -94,7 +95,8 @@ struct pb_ctx {
     pb_scratch part_cursors;   // bucket cursors
     pb_scratch small;          // counters and tiny results
     pb_scratch flush;          // L2 flush buffer
-    pb_scratch claim_set;      // cuckoo in-batch dedupe set
+    pb_scratch claim_set;      // cuckoo in-batch dedupe set (small batches)
+    pb_scratch claim_bitmap;   // cuckoo in-batch dedupe bitmap, 2^fp_bits bits (large batches); all zero between calls
     void *pinned[2] = {nullptr, nullptr};  // pinned bounce buffers for pageable host memory
     size_t pinned_cap[2] = {0, 0};
     void *pinned_small = nullptr;          // 4 KiB pinned result area

@@ -419,6 +419,7 @@ int pb_ctx_destroy(pb_ctx *ctx) {
     scratch_release(ctx->small);
     scratch_release(ctx->flush);
     scratch_release(ctx->claim_set);
+    scratch_release(ctx->claim_bitmap);
     if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
     for (const pb_timed_launch &t : ctx->timed) {
         cudaEventDestroy(t.e0);
@@ -501,6 +502,7 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "stage_bytes")) return &ctx->stage_bytes;
     if (!strcmp(name, "bloom_apply_cpw_per_sm")) return &ctx->bloom_apply_cpw_per_sm;
     if (!strcmp(name, "bloom_min_chunks")) return &ctx->bloom_min_chunks;
+    if (!strcmp(name, "bloom_check_mode")) return &ctx->bloom_check_mode;
     if (!strcmp(name, "bloom_part_ctas_per_sm")) return &ctx->bloom_part_ctas_per_sm;
     if (!strcmp(name, "bloom_overlap")) return &ctx->bloom_overlap;
     if (!strcmp(name, "bloom_part_tile")) return &ctx->bloom_part_tile;

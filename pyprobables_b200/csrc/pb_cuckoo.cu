@@ -43,8 +43,6 @@ struct pb_cuckoo {
     uint32_t *slots = nullptr;
     uint64_t nslots = 0;
     uint32_t *zero_flag = nullptr;  // device word: 1 when fingerprint 0 is stored
-    uint32_t *claim = nullptr;      // 2^fp_bits bits of in-batch claim scratch (large batches only, allocated on first use)
-    uint64_t claim_words = 0;
     uint64_t *alt = nullptr;        // pre-indexed mode: idx_2 per slot (allocated by the first pre-indexed call)
     uint64_t n_stored = 0;          // host mirror of the number of stored fingerprints is kept by the caller
     FastMod fm;
@@ -465,7 +463,7 @@ static CuckooDev dev_view(const pb_cuckoo *c) {
     CuckooDev d;
     d.slots = c->slots;
     d.zero_flag = c->zero_flag;
-    d.claim = c->claim;
+    d.claim = nullptr;  // chosen per call (add_fps_device)
     d.claim_mask = 0;
     d.alt = c->alt;
     d.fm = c->fm;
@@ -482,18 +480,15 @@ static CuckooDev dev_view(const pb_cuckoo *c) {
         else KERNEL<0><<<GRID, BLOCK, 0, (c)->ctx->stream>>>(__VA_ARGS__);                          \
     } while (0)
 
-static int ensure_claim(pb_cuckoo *c) {
-    if (c->claim) return PB_OK;
-    c->claim_words = c->fp_bits >= 5 ? (1ull << (c->fp_bits - 5)) : 1ull;
-    cudaError_t e = cudaMalloc(&c->claim, c->claim_words * 4);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        c->claim = nullptr;
-        set_error("cudaMalloc of the %llu-byte claim bitmap failed: %s", (unsigned long long)(c->claim_words * 4),
-                  cudaGetErrorString(e));
-        return PB_ERR_OOM;
-    }
-    PB_CUDA(cudaMemsetAsync(c->claim, 0, c->claim_words * 4, c->ctx->stream));
+// The 2^fp_bits-bit claim bitmap lives in the CONTEXT's scratch (one per context, not one per filter) and is all
+// zero between calls: a (re)allocation zeroes it, every user clears what it touched.
+static int ensure_claim(pb_cuckoo *c, uint32_t **bitmap, uint64_t *bytes) {
+    pb_ctx *ctx = c->ctx;
+    *bytes = c->fp_bits >= 5 ? (1ull << (c->fp_bits - 3)) : 4ull;
+    const void *before = ctx->claim_bitmap.p;
+    PB_TRY(scratch_reserve(ctx, ctx->claim_bitmap, *bytes));
+    if (ctx->claim_bitmap.p != before) PB_CUDA(cudaMemsetAsync(ctx->claim_bitmap.p, 0, ctx->claim_bitmap.cap, ctx->stream));
+    *bitmap = (uint32_t *)ctx->claim_bitmap.p;
     return PB_OK;
 }
 
@@ -532,6 +527,7 @@ static int add_fps_device(pb_cuckoo *c, const uint4 *fused_keys, uint32_t *fps_d
         // whose set is smaller than the 2^fp_bits-bit bitmap (512 MiB for 32-bit fingerprints), the bitmap otherwise
         CuckooDev cd2 = dev_view(c);
         const uint64_t bitmap_bytes = c->fp_bits >= 5 ? (1ull << (c->fp_bits - 3)) : 4ull;
+        uint64_t bitmap_bytes_used = 0;
         uint64_t set_entries = 64;
         while (set_entries < 4 * n) set_entries <<= 1;
         const bool use_set = set_entries * 4 < bitmap_bytes;
@@ -541,8 +537,7 @@ static int add_fps_device(pb_cuckoo *c, const uint4 *fused_keys, uint32_t *fps_d
             cd2.claim = (uint32_t *)ctx->claim_set.p;
             cd2.claim_mask = (uint32_t)(set_entries - 1);
         } else {
-            PB_TRY(ensure_claim(c));
-            cd2.claim = c->claim;
+            PB_TRY(ensure_claim(c, &cd2.claim, &bitmap_bytes_used));
         }
         const int grid = grid_for(ctx, n, 256, 8);
         if (fused_keys) PB_BS_DISPATCH(c, cuckoo_claim_fixed16, grid, 256, fused_keys, n, cd2, fps_dev, newlist, cnt);
@@ -550,7 +545,7 @@ static int add_fps_device(pb_cuckoo *c, const uint4 *fused_keys, uint32_t *fps_d
         PB_TRY(check_launch(ctx, "cuckoo_claim"));
         PB_BS_DISPATCH(c, cuckoo_insert_kernel, grid, 256, newlist, &cnt->n_new, 0, 0, cd2, seed, failed, n, cnt);
         PB_TRY(check_launch(ctx, "cuckoo_insert"));
-        if (!use_set) PB_CUDA(cudaMemsetAsync(c->claim, 0, c->claim_words * 4, ctx->stream));
+        if (!use_set) PB_CUDA(cudaMemsetAsync(cd2.claim, 0, bitmap_bytes_used, ctx->stream));
     }
     // results (small D2H; this call is synchronous by contract because failures must be reported)
     CuckooCounters *h = (CuckooCounters *)((uint8_t *)ctx->pinned_small + 256);
@@ -734,7 +729,6 @@ int pb_cuckoo_destroy(pb_cuckoo *c) {
     cudaStreamSynchronize(c->ctx->stream);
     cudaFree(c->slots);
     cudaFree(c->zero_flag);
-    if (c->claim) cudaFree(c->claim);
     if (c->alt) cudaFree(c->alt);
     delete c;
     return PB_OK;

@@ -15,6 +15,7 @@ therefore loads and answers here exactly as it does there.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import math
 import mmap as _mmap
 import struct
@@ -128,7 +129,8 @@ class CuckooFilter:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():  # at interpreter exit the CUDA context may already be gone
+                self.close()
         except Exception:
             pass
 

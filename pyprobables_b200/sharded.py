@@ -20,6 +20,7 @@ and merge() sums them with one all-reduce into a separate merged table -- the re
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import math
 from dataclasses import dataclass
 
@@ -195,7 +196,7 @@ class ShardedBloomFilter:
     every rank hashes everything and applies its own range (any key width)."""
 
     def __init__(self, est_elements, false_positive_rate, group=None, device=None, context=None, chunk_keys: int = 1 << 27,
-                 mode: str = "p2p"):
+                 mode: str = "p2p", window_log2: int = 27):
         import torch
         import torch.distributed as dist
 
@@ -205,7 +206,7 @@ class ShardedBloomFilter:
         self.world = dist.get_world_size(group)
         self._fpr, self._k, self._m = optimized_params(est_elements, false_positive_rate)
         self._est = est_elements
-        self.plan = ShardPlan.make(self._m, self.world)
+        self.plan = ShardPlan.make(self._m, self.world, window_log2)
         self.lo, self.hi = self.plan.bounds(self.rank)
         if device is None:
             device = torch.cuda.current_device()
@@ -261,7 +262,8 @@ class ShardedBloomFilter:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():  # at interpreter exit the CUDA context may already be gone
+                self.close()
         except Exception:
             pass
 

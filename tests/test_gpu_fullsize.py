@@ -68,8 +68,21 @@ def test_bloom_config2_size(env, orc):
 
     _native.call("pb_bloom_pair_popcounts", u._h, whole._h, counts)
     assert counts[0] == counts[1] == bits  # |u OR whole| == |u AND whole| == |whole|  <=>  identical bit arrays
-    # membership: everything inserted is present; absent probes agree with the oracle
-    assert bool(whole.check_many(keys[:5_000_000]).all())
+    # membership: everything inserted is present (30 M device keys: the auto mode samples the hit rate and takes the
+    # partitioned query); absent probes agree with the oracle and with the direct kernel
+    assert bool(whole.check_many(keys[:30_000_000]).all())
+    mixed = torch.cat([keys[:10_000_000], _device_keys(torch, ctx, 10**9, 10_000_000), keys[-5:]])
+    ctx.set_option("bloom_check_mode", 2)
+    try:
+        part = whole.check_many(mixed)
+    finally:
+        ctx.set_option("bloom_check_mode", 1)
+    try:
+        direct = whole.check_many(mixed)
+    finally:
+        ctx.set_option("bloom_check_mode", 0)
+    assert bool((part == direct).all()) and bool(part[:10_000_000].all()) and bool(part[-5:].all())
+    assert int(part[10_000_000:-5].sum()) < 100  # the filter is 4 % full: essentially no false positives
     probe = orc.uniform_keys(10**9, 2_000_000)
     assert (whole.check_many(probe) == ob.check(orc.pack(probe))).all()
     for f in (whole, a, b, u):
