@@ -618,7 +618,7 @@ def run_ours(args) -> None:
         for _ in range(max(args.warmup, 0)):
             step()
         barrier()
-        ctxs = [ctx] + ([filt._ctx_part] if getattr(filt, "_ctx_part", None) is not None else [])
+        ctxs = [ctx] + [c for c in (getattr(filt, "_ctx_part", None), getattr(filt, "_ctx_state", None)) if c is not None]
         for c in ctxs[1:]:
             for kv in args.opt:
                 name, value = kv.split("=")
@@ -632,6 +632,8 @@ def run_ours(args) -> None:
         e0.record(stream)
         for _ in range(args.steps):
             step()
+        if world > 1:
+            filt.join()  # the sharded insert returns after its pass 1: order the stream after the exchange and pass 2 too
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -803,6 +805,7 @@ def run_ours(args) -> None:
                 t0e.record(stream)
                 for _ in range(2):
                     step5()
+                f5.join()
                 t1e.record(stream)
                 barrier()
                 t5 = torch.tensor([t0e.elapsed_time(t1e) / 2], dtype=torch.float64, device=dev)

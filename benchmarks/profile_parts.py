@@ -4,7 +4,7 @@
   ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 2 -o gpurun_out/prof_<part> \
       python benchmarks/profile_parts.py <part>
 
-parts: bloom_insert (bloom_part4 + bloom_apply2), bloom_check (bloom_check_fixed16), bloom_query (bloom_part4<IDS> +
+parts: bloom_insert (bloom_part4 + bloom_apply2), bloom_insert_w286 (the same with 286 windows: the 8-GPU geometry), bloom_check (bloom_check_fixed16), bloom_query (bloom_part4<IDS> +
 bloom_probe2), cms (cms_add_fixed16, cms_check_fixed16), cuckoo (cuckoo_claim_fixed16, cuckoo_insert_kernel,
 cuckoo_check_fixed16), cbloom (cbloom_add_fixed16).  Not a benchmark: numbers taken under a profiler are never reported.
 """
@@ -31,9 +31,11 @@ def main():
         keys = torch.empty((n, 16), dtype=torch.uint8, device="cuda")
         ctx.gen_uniform_keys(0, n, keys.data_ptr())
         kb = pack_keys(keys)
-        if part in ("bloom_insert", "bloom_check", "bloom_query"):
+        if part in ("bloom_insert", "bloom_insert_w286", "bloom_check", "bloom_query"):
             f = pb.BloomFilter(10**9, 0.01, context=ctx)
             ctx.set_option("bloom_insert_mode", 2)
+            if part == "bloom_insert_w286":  # pass 1 with the window count of an 8-GPU run (286 windows, 512-key tiles)
+                ctx.set_option("bloom_window_log2_bits", 25)
             _native.call("pb_bloom_add_keys", f._h, kb.ref())
             if part != "bloom_insert":
                 res = torch.empty(n, dtype=torch.uint8, device="cuda")

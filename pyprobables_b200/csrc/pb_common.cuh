@@ -81,6 +81,7 @@ struct pb_ctx {
     int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics
     int64_t cms_hot_cache = 1;           // per-CTA shared-memory write-back cache for hot counters (safe path)
     int64_t cuckoo_serial = 0;           // 1: one-thread in-order cuckoo insert (reference append order)
+    int64_t p2p_copy_lanes = 4;          // multi-GPU exchange: streams (copy engines) the pushes of one chunk are spread over
     int64_t p2p_timeout_ms = 20000;      // multi-GPU flag waits give up after this long (pb_p2p_check reports it)
     int64_t kernel_timing = 0;           // 1: bracket the hot kernels with CUDA events (bench roofline)
     std::vector<pb_timed_launch> timed;

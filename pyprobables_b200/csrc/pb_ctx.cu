@@ -511,6 +511,7 @@ static int64_t *option_slot(pb_ctx *ctx, const char *name) {
     if (!strcmp(name, "cms_hot_cache")) return &ctx->cms_hot_cache;
     if (!strcmp(name, "cuckoo_serial")) return &ctx->cuckoo_serial;
     if (!strcmp(name, "p2p_timeout_ms")) return &ctx->p2p_timeout_ms;
+    if (!strcmp(name, "p2p_copy_lanes")) return &ctx->p2p_copy_lanes;
     if (!strcmp(name, "kernel_timing")) return &ctx->kernel_timing;
     return nullptr;
 }

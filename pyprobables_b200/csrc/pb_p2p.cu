@@ -35,6 +35,7 @@ pb_ctx *bloom_ctx(pb_bloom *b);
 
 constexpr int kBufs = 3;
 constexpr int kMaxRanks = 16;
+constexpr int kCopyLanes = 4;
 
 struct pb_p2p {
     pb_ctx *send_ctx = nullptr;
@@ -47,6 +48,10 @@ struct pb_p2p {
     uint32_t *lstage[kBufs] = {nullptr, nullptr, nullptr};  // local staging [world*wps][n_sub][sub_cap], allocated on first use
     uint64_t send_seq = 0, apply_seq = 0;
     cudaStream_t copy_stream = nullptr;
+    // the pushes of one chunk are spread over several streams so that several copy engines work at once (one
+    // cudaMemcpyAsync at a time does not fill NVLink: r2, N = 8 was bound by the serialised pushes)
+    cudaStream_t copy_lane[kCopyLanes] = {nullptr};
+    cudaEvent_t ev_lane_go = nullptr, ev_lane_done[kCopyLanes] = {nullptr};
     cudaEvent_t ev_part[kBufs] = {nullptr, nullptr, nullptr}, ev_copy[kBufs] = {nullptr, nullptr, nullptr};
 };
 
@@ -176,6 +181,11 @@ int pb_p2p_create(pb_ctx *send_ctx, uint32_t world, uint32_t rank, uint32_t wind
         PB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[h], cudaEventDisableTiming));
     }
     PB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    PB_CUDA(cudaEventCreateWithFlags(&p->ev_lane_go, cudaEventDisableTiming));
+    for (int l = 0; l < kCopyLanes; ++l) {
+        PB_CUDA(cudaStreamCreateWithFlags(&p->copy_lane[l], cudaStreamNonBlocking));
+        PB_CUDA(cudaEventCreateWithFlags(&p->ev_lane_done[l], cudaEventDisableTiming));
+    }
     // flags and counts start at zero; the lists need no initialisation
     PB_CUDA(cudaMemset(p->local + kBufs * p->stage_bytes, 0, kBufs * p->cnt_bytes + kFlagBytes));
     p->peer[rank] = p->local;
@@ -261,6 +271,11 @@ int pb_p2p_destroy(pb_p2p *p) {
         if (p->ev_copy[h]) cudaEventDestroy(p->ev_copy[h]);
     }
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->ev_lane_go) cudaEventDestroy(p->ev_lane_go);
+    for (int l = 0; l < kCopyLanes; ++l) {
+        if (p->copy_lane[l]) cudaStreamDestroy(p->copy_lane[l]);
+        if (p->ev_lane_done[l]) cudaEventDestroy(p->ev_lane_done[l]);
+    }
     cudaFree(p->local);
     delete p;
     return PB_OK;
@@ -336,12 +351,22 @@ int pb_p2p_partition_send(pb_p2p *p, const pb_keys *keys, uint64_t num_bits, uin
     PB_CUDA(cudaEventRecord(p->ev_part[h], ctx->stream));
     PB_CUDA(cudaStreamWaitEvent(cs, p->ev_part[h], 0));
     if (seq > kBufs) PB_TRY(launch_wait(p, ctx, cs, off_done_flag(p, h), seq - kBufs));  // every owner applied what this buffer held
+    launch_begin(ctx, cs);  // "p2p_copy" in pb_ctx_kernel_times: the pushes of this chunk, first byte to last
+    PB_CUDA(cudaEventRecord(p->ev_lane_go, cs));
+    const int lanes = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->p2p_copy_lanes, kCopyLanes));
+    for (int l = 0; l < lanes; ++l) PB_CUDA(cudaStreamWaitEvent(p->copy_lane[l], p->ev_lane_go, 0));
     for (uint32_t i = 0; i < p->world; ++i) {
         const uint32_t d = (p->rank + 1 + i) % p->world;  // stagger the destinations across ranks
         PB_CUDA(cudaMemcpyAsync(p->peer[d] + off_stage(p, h) + (size_t)p->rank * block_bytes,
                                 reinterpret_cast<const uint8_t *>(p->lstage[h]) + (size_t)d * block_bytes, block_bytes,
-                                cudaMemcpyDeviceToDevice, cs));
+                                cudaMemcpyDeviceToDevice, p->copy_lane[i % lanes]));
     }
+    for (int l = 0; l < lanes; ++l) {
+        PB_CUDA(cudaEventRecord(p->ev_lane_done[l], p->copy_lane[l]));
+        PB_CUDA(cudaStreamWaitEvent(cs, p->ev_lane_done[l], 0));
+    }
+    PB_TRY(check_launch(ctx, "p2p_copy", cs));
+    ctx->launches--;  // (not a kernel)
     p2p_publish<<<p->world, 256, 0, cs>>>(peers_of(p), p->scnt[h], p->wps * p->n_sub, p->rank, off_cnt(p, h), off_data_flag(p, h), seq);
     PB_TRY(check_launch(ctx, "p2p_publish", cs));
     PB_CUDA(cudaEventRecord(p->ev_copy[h], cs));
