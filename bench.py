@@ -685,10 +685,11 @@ def run_ours(args) -> None:
             tj = ncu_traffic()
             traffic, traffic_src = None, None
             try:
-                per_key = sum((tj[kn]["dram_bytes_read"] + tj[kn]["dram_bytes_write"]) / tj[kn]["keys_per_launch"]
-                              for kn in ("bloom_part", "bloom_apply_windows"))
-                traffic = per_key * n_keys
-                traffic_src = f"{tj['_file']}: {per_key:.1f} DRAM B/key (both passes, ncu --set full) x {n_keys} keys per step"
+                per_key = tj["bloom_part"]["dram_bytes_per_key"] + tj["bloom_apply_windows"]["list_dram_bytes_per_key"]
+                sweep = tj["bloom_apply_windows"]["bitmap_sweep_bytes_per_launch"] * chunks_per_step if world == 1 else 2.0 * bitmap_bytes * chunks_per_step
+                traffic = per_key * n_keys + sweep
+                traffic_src = (f"{tj['_file']} (ncu --set full, dram__bytes_read+write): {per_key:.1f} DRAM B/key for keys + staged lists "
+                               f"x {n_keys} keys + one read+write of the bit array per chunk x {chunks_per_step} chunks")
             except Exception:
                 pass
             dom = max(ktimes.items(), key=lambda kv: kv[1][1])[0]

@@ -33,7 +33,7 @@ def main():
         kb = pack_keys(keys)
         if part in ("bloom_insert", "bloom_insert_w286", "bloom_check", "bloom_query"):
             f = pb.BloomFilter(10**9, 0.01, context=ctx)
-            ctx.set_option("bloom_insert_mode", 2)
+            ctx.set_option("bloom_insert_mode", 1 if part == "bloom_query" else 2)  # (query capture: no pass-1 launches before it)
             if part == "bloom_insert_w286":  # pass 1 with the window count of an 8-GPU run (286 windows, 512-key tiles)
                 ctx.set_option("bloom_window_log2_bits", 25)
             _native.call("pb_bloom_add_keys", f._h, kb.ref())
@@ -50,10 +50,10 @@ def main():
             est = torch.empty(n, dtype=torch.int64, device="cuda")
             _native.call("pb_cms_check_keys", c._h, kb.ref(), 0, n, C.c_void_p(est.data_ptr()), 1)
         elif part == "cuckoo":
-            cap = 1 << 26
+            cap = 1 << 25  # 125 M keys -> 93 % load: the second batch shows the eviction regime
             f = pb.CuckooFilter(capacity=cap, bucket_size=4, max_swaps=500, auto_expand=False, context=ctx)
             step = 1 << 26
-            for lo in range(0, min(n, int(cap * 4 * 0.9)), step):  # up to ~90 % load: the later launches show the eviction regime
+            for lo in range(0, n, step):
                 f.add_many(keys[lo : min(lo + step, n)])
             f.check_many(keys[:step])
         elif part == "cbloom":

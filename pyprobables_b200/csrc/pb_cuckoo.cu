@@ -10,12 +10,12 @@
 // reference's own export format, :346/:429); it is kept as a one-word device flag.
 //
 // add() for a batch runs as three kernels:
-//   1. claim+filter  hash key -> fp (:499-500); one thread per *distinct* fp of the batch wins a claim
+//   1. claim+place   hash key -> fp (:499-500); one thread per *distinct* fp of the batch wins a claim
 //                    (an exact set in scratch memory: one atomicCAS / atomicOr per key); the winner
-//                    looks the fp up in its two buckets (:300-302, :440-446) and, when absent, appends
-//                    it to a compact list of fingerprints to insert.
-//   2. insert        one thread per new fp: CAS into the first empty slot of idx_1, then idx_2
-//                    (:363-368); otherwise the eviction walk of <= max_swaps steps (:371-389) with
+//                    looks the fp up in its two buckets (:300-302, :440-446) and, when absent, tries the
+//                    first empty slot of idx_1, then idx_2 (:363-368) from the same bucket snapshots; only
+//                    fingerprints whose two buckets are full go to a compact list for kernel 2.
+//   2. evict         one thread per listed fp: (re-try both buckets, then) the eviction walk of <= max_swaps steps (:371-389) with
 //                    atomicExch -- every fingerprint is always either in a slot or in exactly one
 //                    thread's hand, so nothing is duplicated or lost.  Walks that run out of swaps hand
 //                    their homeless fingerprint back to the caller (:392, :508-516).
@@ -166,25 +166,44 @@ __device__ __forceinline__ bool cuckoo_insert_one(const CuckooDev &c, uint32_t &
 template <int BS>
 __device__ __forceinline__ void claim_filter(const CuckooDev &c, uint32_t fp, bool active, uint32_t *__restrict__ newlist,
                                              CuckooCounters *cnt) {
-    bool is_new = false;
+    bool is_new = false;   // still homeless after the first try: goes to the eviction kernel
+    uint32_t placed = 0;
     if (active) {
         if (fp == 0u) {
             // the zero fingerprint lives in the flag word; the flag itself is the claim
-            if (atomicExch(c.zero_flag, 1u) == 0u) atomicAdd(&cnt->n_placed, 1ull);
-        } else {
-            if (claim_fp(c, fp)) {  // this thread owns fp for the batch
-                uint64_t i1, i2;
-                cuckoo_buckets(c, fp, i1, i2);
-                const bool in1 = bucket_has<BS>(c, i1, fp);  // both probes in flight together (no short circuit)
+            if (atomicExch(c.zero_flag, 1u) == 0u) placed = 1;
+        } else if (claim_fp(c, fp)) {  // this thread owns fp for the batch
+            uint64_t i1, i2;
+            cuckoo_buckets(c, fp, i1, i2);
+            if (BS == 4) {
+                // both buckets in flight together; the snapshots serve the presence test (:300-302) AND the first
+                // placement attempt (:363-368): the CAS hits the sector the load has just brought into L2, and the
+                // second kernel only ever sees fingerprints whose two buckets were full (r2: it used to re-read both
+                // buckets of every new fingerprint from DRAM)
+                const uint4 v1 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i1);
+                const uint4 v2 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i2);
+                const bool in1 = v1.x == fp || v1.y == fp || v1.z == fp || v1.w == fp;
+                const bool in2 = v2.x == fp || v2.y == fp || v2.z == fp || v2.w == fp;
+                if (!(in1 | in2)) {
+                    if (bucket_place_from(c, i1, fp, v1) || bucket_place_from(c, i2, fp, v2)) placed = 1;
+                    else is_new = true;
+                }
+            } else {
+                const bool in1 = bucket_has<BS>(c, i1, fp);
                 const bool in2 = bucket_has<BS>(c, i2, fp);
-                is_new = !(in1 | in2);  // :300-302
+                if (!(in1 | in2)) {
+                    if (bucket_place<BS>(c, i1, fp) || bucket_place<BS>(c, i2, fp)) placed = 1;
+                    else is_new = true;
+                }
             }
         }
     }
-    // warp-aggregated append to the list of fingerprints to insert
+    // warp-aggregated counters and append to the list of fingerprints that need the eviction walk
+    const uint32_t pm = __ballot_sync(0xffffffffu, placed != 0);
     const uint32_t m = __ballot_sync(0xffffffffu, is_new);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (pm && lane == (uint32_t)(__ffs(pm) - 1)) atomicAdd(&cnt->n_placed, (unsigned long long)__popc(pm));
     if (m) {
-        const uint32_t lane = threadIdx.x & 31u;
         unsigned long long base = 0;
         if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&cnt->n_new, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
