@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--windows", default="24,25,26,27,28")
     ap.add_argument("--cpw", default="2,4,8")
     ap.add_argument("--modes", default="2")
-    ap.add_argument("--versions", default="3")
+    ap.add_argument("--versions", default="0", help="pass-1 CTAs per SM to sweep (0 = auto)")
     ap.add_argument("--overlap", default="0,1")
     ap.add_argument("--tiles", default="0")
     a = ap.parse_args()
@@ -43,12 +43,12 @@ def main():
                   for o in a.overlap.split(",") for t in a.tiles.split(",")
                   for w, c in itertools.product(a.windows.split(","), a.cpw.split(","))]
         if "1" not in a.modes.split(","):
-            combos.insert(0, (1, 28, 4, 2, 0, 0))
+            combos.insert(0, (1, 28, 4, 0, 0, 0))
         for mode, wl, cpw, ver, ov, tile in combos:
             ctx.set_option("bloom_insert_mode", mode)
             ctx.set_option("bloom_part_tile", tile)
             ctx.set_option("bloom_overlap", ov)
-            ctx.set_option("bloom_part_version", ver)
+            ctx.set_option("bloom_part_ctas_per_sm", ver)  # (the round-1 "version" axis is gone: this axis is now CTAs per SM, 0 = auto)
             ctx.set_option("bloom_window_log2_bits", wl)
             ctx.set_option("bloom_apply_cpw_per_sm", cpw)
             for rep in range(2):
@@ -64,7 +64,7 @@ def main():
             bits = filt._cnt_number_bits_set()
             if ref_bits is None:
                 ref_bits = bits
-            row = {"mode": mode, "version": ver, "overlap": ov, "tile": tile, "window_log2": wl, "cpw_per_sm": cpw, "ms": round(ms, 3), "Gkeys_s": round(a.keys / ms / 1e6, 3),
+            row = {"mode": mode, "part_ctas_per_sm": ver, "overlap": ov, "tile": tile, "window_log2": wl, "cpw_per_sm": cpw, "ms": round(ms, 3), "Gkeys_s": round(a.keys / ms / 1e6, 3),
                    "kernels_ms": {k: round(v[1], 3) for k, v in kt.items()}, "bits_ok": bits == ref_bits}
             rows.append(row)
             print(json.dumps(row), flush=True)

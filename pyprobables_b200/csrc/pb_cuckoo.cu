@@ -44,7 +44,6 @@ struct pb_cuckoo {
     uint64_t nslots = 0;
     uint32_t *zero_flag = nullptr;  // device word: 1 when fingerprint 0 is stored
     uint64_t *alt = nullptr;        // pre-indexed mode: idx_2 per slot (allocated by the first pre-indexed call)
-    uint64_t n_stored = 0;          // host mirror of the number of stored fingerprints is kept by the caller
     FastMod fm;
 };
 
