@@ -80,7 +80,7 @@ int pb_ctx_kernel_times(pb_ctx *ctx, char *buf, size_t cap);
 /* tuning knobs: "bloom_insert_mode" (0 = auto, 1 = direct RED.OR, 2 = partition + L2-window apply),
  * "bloom_window_log2_bits", "stage_bytes" (staging budget for partitioned insert),
  * "bloom_min_chunks" (chunks a large batch is split into so pass 2 overlaps the next pass 1), "p2p_timeout_ms",
- * "h2d_chunk_keys" (host-buffer pipeline chunk), "cms_aggregate" (warp-combine equal keys, default 1),
+ * "h2d_chunk_keys" (host-buffer pipeline chunk), "cms_aggregate" (warp-combine equal keys: 0 never, 1 always, 2 = default: only when the hot-counter cache is off),
  * "cuckoo_serial" (1 = one-thread in-order cuckoo insert that reproduces the reference's append order),
  * "kernel_timing" (1 = bracket hot kernels with events, see pb_ctx_kernel_times). */
 int pb_ctx_set_option(pb_ctx *ctx, const char *name, int64_t value);

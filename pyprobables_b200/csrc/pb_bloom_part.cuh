@@ -303,21 +303,30 @@ static __global__ void __launch_bounds__(256) bloom_probe2(PartDev p, uint32_t c
             const uint32_t n = min(kApplyTile, cnt - i * kApplyTile);
             const uint4 *l4 = reinterpret_cast<const uint4 *>(sm.loc[st]);
             const uint4 *i4 = reinterpret_cast<const uint4 *>(sm.id[st]);
+            // all eight probes of a thread are in flight before the first one is tested (the loads return through L2:
+            // unlike pass 2's REDs they are not fire-and-forget, so memory-level parallelism per thread decides)
+            constexpr uint32_t Q = kApplyTile / 4 / 256;
+            uint32_t loc[Q][4], wd[Q][4];
 #pragma unroll
-            for (uint32_t q = 0; q < kApplyTile / 4 / 256; ++q) {
+            for (uint32_t q = 0; q < Q; ++q) {
                 const uint32_t e = (q * 256 + threadIdx.x) * 4;
-                if (e < n) {
-                    const uint4 v = l4[q * 256 + threadIdx.x];
+                const uint4 v = l4[q * 256 + threadIdx.x];
+                loc[q][0] = v.x, loc[q][1] = v.y, loc[q][2] = v.z, loc[q][3] = v.w;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) wd[q][j] = e + j < n ? __ldg(words + (loc[q][j] >> 5)) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < Q; ++q) {
+                const uint32_t e = (q * 256 + threadIdx.x) * 4;
+                bool any = false;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) any |= e + j < n && !((wd[q][j] >> (loc[q][j] & 31)) & 1u);
+                if (any) {  // rare for members: only then are the key numbers read
                     const uint4 k = i4[q * 256 + threadIdx.x];
-                    // the four loads are issued before any of them is tested
-                    const uint32_t w0 = __ldg(words + (v.x >> 5));
-                    const uint32_t w1 = e + 1 < n ? __ldg(words + (v.y >> 5)) : 0xFFFFFFFFu;
-                    const uint32_t w2 = e + 2 < n ? __ldg(words + (v.z >> 5)) : 0xFFFFFFFFu;
-                    const uint32_t w3 = e + 3 < n ? __ldg(words + (v.w >> 5)) : 0xFFFFFFFFu;
-                    if (!((w0 >> (v.x & 31)) & 1u)) p.out[k.x] = 0;
-                    if (e + 1 < n && !((w1 >> (v.y & 31)) & 1u)) p.out[k.y] = 0;
-                    if (e + 2 < n && !((w2 >> (v.z & 31)) & 1u)) p.out[k.z] = 0;
-                    if (e + 3 < n && !((w3 >> (v.w & 31)) & 1u)) p.out[k.w] = 0;
+                    const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j)
+                        if (e + j < n && !((wd[q][j] >> (loc[q][j] & 31)) & 1u)) p.out[kk[j]] = 0;
                 }
             }
             __syncthreads();

@@ -78,7 +78,7 @@ struct pb_ctx {
     int64_t bloom_min_chunks = 8;        // overlapped partitioned insert: split a batch into at least this many chunks
     int64_t stage_bytes = 8ll << 30;     // staging budget for partitioned insert
     int64_t h2d_chunk_keys = 1ll << 24;  // keys per H2D pipeline chunk
-    int64_t cms_aggregate = 1;           // warp-aggregate equal keys before the atomics
+    int64_t cms_aggregate = 2;           // warp-aggregate equal keys before the atomics: 0 never, 1 always, 2 auto (only without the hot cache)
     int64_t cms_hot_cache = 1;           // per-CTA shared-memory write-back cache for hot counters (safe path)
     int64_t cuckoo_serial = 0;           // 1: one-thread in-order cuckoo insert (reference append order)
     int64_t p2p_copy_lanes = 4;          // multi-GPU exchange: streams (copy engines) the pushes of one chunk are spread over
