@@ -180,6 +180,17 @@ int pb_bloom_and_rows(pb_ctx *ctx, const uint8_t *bits_dev, uint64_t n, uint32_t
 int pb_bloom_add_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n);
 int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, uint8_t *out_dev);
 
+/* Ordered "check, then add" batches: ExpandingBloomFilter / RotatingBloomFilter.add_alt (blooms/expandingbloom.py:159-169,
+ * :320-330) add a key to the newest filter of the stack only if no filter finds it.  Rows = k bit indices per key
+ * (pb_bloom_index_keys, or plugin hashes reduced mod num_bits), all on the device.
+ * pb_bloom_novel_rows: novel_dev[i] = 1 iff adding the rows one at a time, in order, would add row i to this filter
+ *   (rows with skip_dev[i] != 0 -- found in an older filter -- take no part; skip_dev may be NULL).  Read-only on the
+ *   bits; keeps a 4-byte-per-bit table on the handle until pb_bloom_release_scratch.
+ * pb_bloom_add_rows: bloom.py:241-250 for the rows with mask_dev[i] != 0 (NULL: all rows). */
+int pb_bloom_novel_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *skip_dev, uint8_t *novel_dev);
+int pb_bloom_add_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *mask_dev);
+int pb_bloom_release_scratch(pb_bloom *b);
+
 /* ---------------------------------------------------------------- Counting Bloom (blooms/countingbloom.py) */
 /* state = uint32[num_counters] (array('I'), bloom_length == number_bits, countingbloom.py:77-78);
  * counter of hash i = h_i % num_counters (:143). */

@@ -235,6 +235,57 @@ class Bloom:
         return lib().orc_popcount(self.bloom.ctypes.data, self.bloom.size)
 
 
+class ExpandingBloom:
+    """probables/blooms/expandingbloom.py:149-183 one key at a time (pure-Python loop over precomputed hash rows:
+    small cases only).  `max_queue_size` set = RotatingBloomFilter (:320-361)."""
+
+    def __init__(self, est_elements: int, fpr: float, max_queue_size: int | None = None):
+        self.est_elements, self.fpr = est_elements, fpr
+        _, self.k, self.num_bits, _ = bloom_params(est_elements, fpr)
+        self.max_queue_size = max_queue_size
+        self.blooms: list[Bloom] = [Bloom(self.num_bits, self.k)]
+        self.elements_added = 0
+
+    def _has(self, blm: Bloom, idx) -> bool:  # bloom.py:261-272
+        return all((blm.bloom[i >> 3] >> (i & 7)) & 1 for i in idx)
+
+    def _grow_if_full(self):
+        last = self.blooms[-1]
+        if self.max_queue_size is None:
+            if last.elements_added >= self.est_elements:  # :180-183
+                self.blooms.append(Bloom(self.num_bits, self.k))
+        elif last.elements_added == self.est_elements:  # :350
+            if len(self.blooms) >= self.max_queue_size:  # :351, :359-361
+                self.blooms.pop(0)
+            self.blooms.append(Bloom(self.num_bits, self.k))
+
+    def push(self):  # :126-128, :343-345
+        if self.max_queue_size is not None and len(self.blooms) >= self.max_queue_size:
+            self.blooms.pop(0)
+        self.blooms.append(Bloom(self.num_bits, self.k))
+
+    def add(self, keys: Keys, force: bool = False):
+        rows = default_fnv_1a_many(keys, self.k) % np.uint64(self.num_bits)
+        for row in rows.tolist():
+            self.elements_added += 1  # :166
+            if force or not any(self._has(b, row) for b in self.blooms):  # :167
+                self._grow_if_full()  # :168
+                last = self.blooms[-1]
+                for i in row:  # bloom.py:241-250
+                    last.bloom[i >> 3] |= 1 << (i & 7)
+                last.elements_added += 1
+
+    def check(self, keys: Keys) -> np.ndarray:  # :130-147
+        rows = default_fnv_1a_many(keys, self.k) % np.uint64(self.num_bits)
+        return np.array([any(self._has(b, row) for b in self.blooms) for row in rows.tolist()], dtype=bool)
+
+    def export(self) -> bytes:  # :185-207
+        import struct
+
+        out = b"".join(struct.pack("Q", b.elements_added) + b.bloom.tobytes() for b in self.blooms)
+        return out + struct.pack("QQQf", len(self.blooms), self.est_elements, self.elements_added, self.fpr)
+
+
 class CountingBloom:
     """probables/blooms/countingbloom.py:125-208 on a numpy uint32 array (one counter per 'bit', so the array
     length equals number_bits, countingbloom.py:37)"""

@@ -1,7 +1,7 @@
 """pyprobables_b200 -- B200-native batch engine for pyprobables' hash-then-scatter hot path.
 
 Same class names, constructor arguments, properties, exceptions and `hash_function` plugin seam as
-`probables` (barrust/pyprobables v0.7.0) for BloomFilter, CountingBloomFilter, CountMinSketch (+Mean, +MeanMin)
+`probables` (barrust/pyprobables v0.7.0) for BloomFilter, CountingBloomFilter, Expanding/RotatingBloomFilter, CountMinSketch (+Mean, +MeanMin)
 and CuckooFilter, with the batch methods `add_many` / `check_many` added.  State lives in GPU memory; every
 add/check runs in hand-written sm_100a CUDA kernels behind the C ABI of include/pb200.h.
 There is no CPU fallback: without libpb200.so and a CUDA device the constructors raise.
@@ -13,11 +13,13 @@ from .bloom import BloomFilter
 from .countingbloom import CountingBloomFilter
 from .countminsketch import CountMeanMinSketch, CountMeanSketch, CountMinSketch
 from .cuckoo import CuckooFilter
+from .expandingbloom import ExpandingBloomFilter, RotatingBloomFilter
 from .exceptions import (
     CountMinSketchError,
     CuckooFilterFullError,
     InitializationError,
     NotSupportedError,
+    RotatingBloomFilterError,
     ProbablesBaseException,
     SimilarityError,
 )
@@ -28,6 +30,9 @@ __version__ = "0.1.0"
 __all__ = [
     "BloomFilter",
     "CountingBloomFilter",
+    "ExpandingBloomFilter",
+    "RotatingBloomFilter",
+    "RotatingBloomFilterError",
     "CountMinSketch",
     "CountMeanSketch",
     "CountMeanMinSketch",

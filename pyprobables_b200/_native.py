@@ -124,6 +124,9 @@ SIGNATURES: dict[str, list] = {
     "pb_bloom_and_rows": [_vp, _vp, _u64, _u32, _vp],
     "pb_bloom_add_bit_indices": [_vp, _vp, _u64],
     "pb_bloom_test_bit_indices": [_vp, _vp, _u64, _vp],
+    "pb_bloom_novel_rows": [_vp, _vp, _u64, _vp, _vp],
+    "pb_bloom_add_rows": [_vp, _vp, _u64, _vp],
+    "pb_bloom_release_scratch": [_vp],
     "pb_cbloom_create": [_vp, _u64, _u32, _P(_vp)],
     "pb_cbloom_destroy": [_vp],
     "pb_cbloom_clear": [_vp],

@@ -33,6 +33,7 @@ struct pb_bloom {
     uint64_t nbytes = 0;  // ceil((hi-lo)/8)
     uint64_t nwords = 0;  // allocation, multiple of 4 words
     FastMod fm;
+    uint32_t *first_setter = nullptr;  // check-then-add batches: per owned bit, lowest row that would set it (all ~0u between calls)
 };
 
 namespace pb {
@@ -177,6 +178,61 @@ __global__ void __launch_bounds__(256)
         }
         out[i] = (uint8_t)bit;
     }
+}
+
+// ---- ordered "check, then add" batches (ExpandingBloomFilter.add_alt, expandingbloom.py:159-169) ------------------
+// One key at a time the reference adds key i to the newest filter iff key i is not found when its turn comes.  Keys
+// that are found add nothing new (all their bits are set already), so the bits set before key i's turn are the
+// filter's bits plus the bits of ALL earlier rows that are not skipped, and key i is added iff it owns a bit that is
+// clear in the filter and that no earlier row touches: first_setter[bit] = min row over the batch, then one compare.
+__global__ void __launch_bounds__(256)
+    bloom_first_setter_kernel(const uint64_t *__restrict__ idx, uint64_t n_entries, uint32_t k, BloomDev b,
+                              const uint8_t *__restrict__ skip, uint32_t *__restrict__ first) {
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = e / k;
+        if (skip && skip[row]) continue;
+        const uint64_t l = __ldcs(idx + e) - b.lo;
+        if (!((__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u)) atomicMin(first + l, (uint32_t)row);
+    }
+}
+__global__ void __launch_bounds__(256)
+    bloom_novel_rows_kernel(const uint64_t *__restrict__ idx, uint64_t n, uint32_t k, BloomDev b,
+                            const uint8_t *__restrict__ skip, const uint32_t *__restrict__ first, uint8_t *__restrict__ novel) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t nv = 0;
+        if (!(skip && skip[i])) {
+            for (uint32_t s = 0; s < k; ++s) {
+                const uint64_t l = idx[i * k + s] - b.lo;
+                const bool clear = !((__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u);
+                nv |= (clear && __ldcg(first + l) == (uint32_t)i) ? 1u : 0u;
+            }
+        }
+        novel[i] = (uint8_t)nv;
+    }
+}
+__global__ void __launch_bounds__(256)
+    bloom_first_setter_reset_kernel(const uint64_t *__restrict__ idx, uint64_t n_entries, BloomDev b, uint32_t *__restrict__ first) {
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x)
+        first[__ldcs(idx + e) - b.lo] = 0xFFFFFFFFu;
+}
+// rows [0, n) of k bit indices each; a row is applied iff mask[row] != 0 (mask NULL: every row)
+__global__ void __launch_bounds__(256)
+    bloom_add_rows_kernel(const uint64_t *__restrict__ idx, uint64_t n_entries, uint32_t k, BloomDev b,
+                          const uint8_t *__restrict__ mask) {
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[e / k]) continue;
+        const uint64_t l = __ldcs(idx + e) - b.lo;
+        atomicOr(b.words + (l >> 5), 1u << (uint32_t)(l & 31));
+    }
+}
+__global__ void __launch_bounds__(256)
+    bloom_rows_in_range_kernel(const uint64_t *__restrict__ idx, uint64_t n_entries, BloomDev b, unsigned long long *stray) {
+    unsigned long long bad = 0;
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = idx[e];
+        bad += (g < b.lo || g >= b.hi) ? 1ull : 0ull;
+    }
+    if (bad) atomicAdd(stray, bad);
 }
 
 // bloom.py:371-428: res = a | b (op 0) or a & b (op 1), streaming 128-bit words
@@ -559,6 +615,7 @@ int pb_bloom_destroy(pb_bloom *b) {
     DeviceGuard g(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaFree(b->words);
+    cudaFree(b->first_setter);
     delete b;
     return PB_OK;
 }
@@ -944,6 +1001,75 @@ int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, 
     DeviceGuard g(ctx->device);
     bloom_test_idx_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, dev_view(b), out_dev);
     return check_launch(ctx, "bloom_test_bit_indices");
+}
+
+// every index must fall into the bits this handle owns (the kernels below subtract lo_bit unchecked)
+static int rows_in_range(pb_bloom *b, const uint64_t *idx_dev, uint64_t n_entries) {
+    pb_ctx *ctx = b->ctx;
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *stray = (unsigned long long *)ctx->small.p + 8;
+    PB_CUDA(cudaMemsetAsync(stray, 0, 8, ctx->stream));
+    bloom_rows_in_range_kernel<<<grid_for(ctx, n_entries, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n_entries, dev_view(b), stray);
+    PB_TRY(check_launch(ctx, "bloom_rows_in_range"));
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, stray, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t bad = *(uint64_t *)ctx->pinned_small;
+    PB_REQUIRE(bad == 0, "%llu bit indices fall outside the bits of this filter", (unsigned long long)bad);
+    return PB_OK;
+}
+
+// novel_dev[i] = 1 iff the reference, adding the rows one at a time in order with "add only if not found"
+// (expandingbloom.py:166-169), would add row i to THIS filter.  Rows with skip_dev[i] != 0 take no part (found in an
+// older filter of the stack).  The filter itself is not modified.
+int pb_bloom_novel_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *skip_dev, uint8_t *novel_dev) {
+    PB_REQUIRE(b && ((idx_dev && novel_dev) || n == 0), "NULL argument");
+    PB_REQUIRE(n < 0xFFFFFFFFull, "at most 2^32 - 2 rows per call");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    const uint64_t n_entries = n * b->k;
+    PB_TRY(rows_in_range(b, idx_dev, n_entries));
+    if (!b->first_setter) {
+        PB_CUDA(cudaMalloc(&b->first_setter, b->nwords * 32 * sizeof(uint32_t)));
+        PB_CUDA(cudaMemsetAsync(b->first_setter, 0xFF, b->nwords * 32 * sizeof(uint32_t), ctx->stream));
+    }
+    const BloomDev bd = dev_view(b);
+    const int ge = grid_for(ctx, n_entries, 256, 8);
+    launch_begin(ctx);
+    bloom_first_setter_kernel<<<ge, 256, 0, ctx->stream>>>(idx_dev, n_entries, b->k, bd, skip_dev, b->first_setter);
+    PB_TRY(check_launch(ctx, "bloom_first_setter"));
+    launch_begin(ctx);
+    bloom_novel_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, b->k, bd, skip_dev, b->first_setter, novel_dev);
+    PB_TRY(check_launch(ctx, "bloom_novel_rows"));
+    launch_begin(ctx);
+    bloom_first_setter_reset_kernel<<<ge, 256, 0, ctx->stream>>>(idx_dev, n_entries, bd, b->first_setter);
+    return check_launch(ctx, "bloom_first_setter_reset");
+}
+
+// BloomFilter.add_alt (bloom.py:241-250) for the rows whose mask byte is non-zero (NULL: all rows); the caller keeps
+// elements_added
+int pb_bloom_add_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *mask_dev) {
+    PB_REQUIRE(b && (idx_dev || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    const uint64_t n_entries = n * b->k;
+    PB_TRY(rows_in_range(b, idx_dev, n_entries));
+    launch_begin(ctx);
+    bloom_add_rows_kernel<<<grid_for(ctx, n_entries, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n_entries, b->k, dev_view(b), mask_dev);
+    return check_launch(ctx, "bloom_add_rows");
+}
+
+// drops the first-setter table of pb_bloom_novel_rows (4 bytes per bit; a filter that stopped being the newest of
+// its stack never needs it again)
+int pb_bloom_release_scratch(pb_bloom *b) {
+    PB_REQUIRE(b, "handle is NULL");
+    if (!b->first_setter) return PB_OK;
+    DeviceGuard g(b->ctx->device);
+    PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    PB_CUDA(cudaFree(b->first_setter));
+    b->first_setter = nullptr;
+    return PB_OK;
 }
 
 }  // extern "C"

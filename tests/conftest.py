@@ -23,6 +23,7 @@ def pytest_configure(config):
 def golden():
     g = json.loads((ROOT / "tests" / "golden" / "golden.json").read_text())
     g.update(json.loads((ROOT / "tests" / "golden" / "golden_r2.json").read_text()))  # round-2 additions (make_golden_r2.py)
+    g.update(json.loads((ROOT / "tests" / "golden" / "golden_r2_wrappers.json").read_text()))  # make_golden_r2_wrappers.py
     return g
 
 

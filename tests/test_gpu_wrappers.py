@@ -1,0 +1,188 @@
+"""Stateful wrappers on the device: ExpandingBloomFilter / RotatingBloomFilter batches against the
+reference's test literals, vectors recorded from the pure-Python reference (tests/golden/make_golden_r2_wrappers.py)
+and the oracle's one-key-at-a-time loop.  A batch must reach exactly the state the reference reaches adding the keys
+one by one: bitmaps, per-filter counts, number of filters and the exported bytes."""
+
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def md5(b):
+    return hashlib.md5(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pyprobables_b200 as p
+
+    assert p.device_count() >= 1
+    return p
+
+
+def stack_state(f) -> dict:
+    return {"n_blooms": len(f._blooms), "per_bloom_added": [b.elements_added for b in f._blooms],
+            "per_bloom_md5": [md5(b.bloom_numpy().tobytes()) for b in f._blooms], "elements_added": f.elements_added,
+            "export_md5": md5(bytes(f))}
+
+
+def oracle_state(o) -> dict:
+    return {"n_blooms": len(o.blooms), "per_bloom_added": [b.elements_added for b in o.blooms],
+            "per_bloom_md5": [md5(b.bloom.tobytes()) for b in o.blooms], "elements_added": o.elements_added,
+            "export_md5": md5(o.export())}
+
+
+def test_expanding_reference_literals(pb, golden):
+    # tests/expandingbloom_test.py:25-54: one batch == 120 single adds
+    e = pb.ExpandingBloomFilter(est_elements=10, false_positive_rate=0.05)
+    assert (e.expansions, e.false_positive_rate, e.estimated_elements, e.elements_added) == (0, 0.05, 10, 0)
+    e.add_many([f"{i}" for i in range(120)])
+    assert e.expansions == 8 and e.elements_added == 120 and stack_state(e) == golden["ebf_120_no_force"]
+    one = pb.ExpandingBloomFilter(est_elements=10, false_positive_rate=0.05)
+    for i in range(120):
+        one.add(f"{i}")
+    assert stack_state(one) == golden["ebf_120_no_force"]
+    f = pb.ExpandingBloomFilter(est_elements=10, false_positive_rate=0.05)
+    f.add_many([f"{i}" for i in range(100)], force=True)
+    assert f.expansions == 9 and stack_state(f) == golden["ebf_100_force"]
+    # :56-83 check / contains
+    c = pb.ExpandingBloomFilter(est_elements=30, false_positive_rate=0.05)
+    c.add_many([f"{i}" for i in range(100)])
+    c.add("this is a test")
+    c.add("this is another test")
+    assert c.expansions > 1 and c.elements_added == 102
+    assert c.check("this is a test") and "this is another test" in c
+    assert not c.check("this is yet another test!") and "this is not another test" not in c
+    # :85-97 push; :99-137 wire format
+    p = pb.ExpandingBloomFilter(est_elements=25, false_positive_rate=0.05)
+    assert md5(bytes(p)) == "eb5769ae9babdf7b37d6ce64d58812bc"
+    p.push(), p.push(), p.push()
+    assert p.expansions == 3 and p.elements_added == 0
+    back = pb.ExpandingBloomFilter.frombytes(bytes(c))
+    assert bytes(back) == bytes(c) and back.check("this is a test") and back.expansions == c.expansions
+    assert back.elements_added == 102 and not back.check("this is yet another test!")
+
+
+def test_expanding_stream_vs_reference_and_oracle(pb, orc, golden):
+    g = golden["ebf_stream"]
+    keys = np.concatenate([orc.uniform_keys(0, g["n_unique"]), orc.uniform_keys(0, g["n_repeat"])])
+    e = pb.ExpandingBloomFilter(est_elements=g["est"], false_positive_rate=g["fpr"])
+    for q in range(4):
+        e.add_many(keys[q * 6250 : (q + 1) * 6250])
+        assert stack_state(e) == g["quarters"][q]
+    hits = np.flatnonzero(e.check_many(orc.uniform_keys(100000, 2000))) + 100000
+    assert hits.tolist() == g["probe_hits_100000_102000"]
+    # the whole stream as ONE batch, from a CUDA tensor, reaches the same state
+    import torch
+
+    one = pb.ExpandingBloomFilter(est_elements=g["est"], false_positive_rate=g["fpr"])
+    one.add_many(torch.from_numpy(keys).cuda())
+    assert stack_state(one) == g["quarters"][3]
+    res = one.check_many(torch.from_numpy(keys[:5000]).cuda())
+    assert res.is_cuda and bool(res.all())
+
+
+@pytest.mark.parametrize("est,fpr,n,dup_every", [(50_000, 0.01, 400_000, 7), (1000, 0.2, 30_000, 0), (3, 0.3, 500, 2)])
+def test_expanding_batch_equals_one_at_a_time(pb, orc, est, fpr, n, dup_every):
+    """larger batches against the oracle loop: many growth steps inside one batch, high false-positive rates (keys
+    skipped because of earlier keys of the same batch), repeated keys"""
+    keys = orc.uniform_keys(10_000, n)
+    if dup_every:
+        keys[::dup_every] = keys[0 : len(keys[::dup_every])]  # repeats of early keys all over the batch
+    e = pb.ExpandingBloomFilter(est_elements=est, false_positive_rate=fpr)
+    o = orc.ExpandingBloom(est, fpr)
+    half = n // 3
+    e.add_many(keys[:half]), o.add(orc.pack(keys[:half]))
+    assert stack_state(e) == oracle_state(o)
+    e.add_many(keys[half:]), o.add(orc.pack(keys[half:]))
+    assert stack_state(e) == oracle_state(o)
+    probes = orc.uniform_keys(5_000_000, 20_000)
+    assert (e.check_many(probes) == o.check(orc.pack(probes))).all()
+
+
+def test_expanding_ragged_str_and_plugin_hash(pb, orc):
+    words = [f"word-{i}-{'x' * (i % 13)}" for i in range(5000)]
+    e = pb.ExpandingBloomFilter(est_elements=400, false_positive_rate=0.05)
+    e.add_many(words)
+    o = orc.ExpandingBloom(400, 0.05)
+    o.add(orc.pack(words))
+    assert stack_state(e) == oracle_state(o)
+
+    def shifted(key, depth):  # a user hash_function: the k-seed FNV of the key with a suffix
+        return pb.hashes.default_fnv_1a(key + "#", depth)
+
+    p = pb.ExpandingBloomFilter(est_elements=400, false_positive_rate=0.05, hash_function=shifted)
+    p.add_many(words)
+    o = orc.ExpandingBloom(400, 0.05)
+    o.add(orc.pack([w + "#" for w in words]))
+    assert stack_state(p) == oracle_state(o)
+    assert p.check(words[17]) and p.check_alt(shifted(words[17], p._blooms[0].number_hashes))
+    p.add_alt(shifted("brand new", p._blooms[0].number_hashes))
+    assert p.check("brand new") and p.elements_added == 5001
+
+
+def test_rotating_stream_vs_reference(pb, orc, golden):
+    g = golden["rbf_stream"]
+    r = pb.RotatingBloomFilter(est_elements=g["est"], false_positive_rate=g["fpr"], max_queue_size=g["queue"])
+    assert r.max_queue_size == g["queue"] and r.current_queue_size == 1
+    for h in range(2):
+        r.add_many(orc.uniform_keys(h * 3000, 3000))
+        assert stack_state(r) == g["halves"][h]
+    present = np.flatnonzero(r.check_many(orc.uniform_keys(0, 6000)[::10])) * 10
+    assert present.tolist() == g["present_step10"]
+    r.push()
+    assert stack_state(r) == g["after_push"]
+    r.pop()
+    assert stack_state(r) == g["after_pop"]
+    r.add_many(orc.uniform_keys(6000, 500), force=True)
+    assert stack_state(r) == g["after_force_500"]
+    back = pb.RotatingBloomFilter.frombytes(bytes(r), max_queue_size=g["queue"])
+    assert bytes(back) == bytes(r) and back.current_queue_size == r.current_queue_size
+    # one batch == the two halves
+    one = pb.RotatingBloomFilter(est_elements=g["est"], false_positive_rate=g["fpr"], max_queue_size=g["queue"])
+    one.add_many(orc.uniform_keys(0, 6000))
+    assert stack_state(one) == g["halves"][1]
+
+
+def test_rotating_reference_literals(pb):
+    # tests/expandingbloom_test.py:168-200
+    blm = pb.RotatingBloomFilter(est_elements=10, false_positive_rate=0.05, max_queue_size=5)
+    blm.add("test")
+    assert blm.expansions == 0
+    blm.add_many([f"{i}" for i in range(10)], force=True)
+    assert blm.expansions == 1 and blm.current_queue_size == 2 and blm.check("test")
+    for lo, q in ((10, 3), (20, 4), (30, 5)):
+        blm.add_many([f"{i}" for i in range(lo, lo + 10)], force=True)
+        assert blm.check("test") and blm.current_queue_size == q
+    blm.add_many([f"{i}" for i in range(40, 50)], force=True)
+    assert not blm.check("test") and blm.current_queue_size == 5 and blm.elements_added == 51
+    # :202-252 push / pop
+    blm = pb.RotatingBloomFilter(est_elements=10, false_positive_rate=0.05, max_queue_size=5)
+    blm.add("test")
+    for q in (2, 3, 4, 5):
+        blm.push()
+        assert blm.current_queue_size == q and "test" in blm
+    blm.push()
+    assert blm.current_queue_size == 5 and "test" not in blm
+    blm.add("that")
+    for q in (4, 3, 2, 1):
+        blm.pop()
+        assert blm.current_queue_size == q and "that" in blm
+    with pytest.raises(pb.RotatingBloomFilterError) as ex:
+        blm.pop()
+    assert str(ex.value) == "Popping a Bloom Filter will result in an unusable system!"
+
+
+@pytest.mark.parametrize("queue", [1, 3])
+def test_rotating_batch_equals_one_at_a_time(pb, orc, queue):
+    keys = orc.uniform_keys(77, 60_000)
+    keys[::5] = keys[0:12_000]
+    r = pb.RotatingBloomFilter(est_elements=2500, false_positive_rate=0.1, max_queue_size=queue)
+    o = orc.ExpandingBloom(2500, 0.1, max_queue_size=queue)
+    r.add_many(keys[:25_000]), o.add(orc.pack(keys[:25_000]))
+    assert stack_state(r) == oracle_state(o)
+    r.add_many(keys[25_000:]), o.add(orc.pack(keys[25_000:]))
+    assert stack_state(r) == oracle_state(o)
