@@ -306,6 +306,28 @@ int pb_cuckoo_capacity(pb_cuckoo *c, uint64_t *out);
  * (PB_ERR_CUCKOO_FULL; the reference raises "The CuckooFilter failed to expand", :463-465). */
 int pb_cuckoo_expand(pb_cuckoo *c, uint64_t new_capacity, uint64_t *n_failed, uint32_t *failed_fps, uint64_t failed_cap);
 
+/* ---------------------------------------------------------------- Counting Cuckoo (cuckoo/countingcuckoo.py) */
+/* A CountingCuckooFilter stores every fingerprint once, next to a count (countingcuckoo.py:156-173).  Here the
+ * fingerprints stay in the pb_cuckoo table (all entry points above apply unchanged) and the counts live in a
+ * fingerprint -> count map on the same handle:
+ *   add    (:156-173)  = pb_cuckoo_add_keys (stores the new fingerprints) + pb_cuckoo_counts_add_keys (+1 per key)
+ *   check  (:175-191)  = pb_cuckoo_counts_get_keys -> uint32 count per key, 0 when absent
+ *   remove (:193-210)  = pb_cuckoo_counts_remove_keys: out[i] = 1 when a count was decremented; a fingerprint whose count
+ *                        reaches 0 leaves the table.  n_removed = decrements, n_bins_removed = fingerprints that left.
+ *   expand (:212-214, :305-316) = pb_cuckoo_expand, then pb_cuckoo_counts_enable again (re-fits the map).
+ * The *_fingerprints variants take host arrays (custom hash_function path, load/export of the (fp, count) bins :216-228,
+ * :286-303); pb_cuckoo_counts_set stores explicit counts (vals NULL: 0 = forget the fingerprint). */
+int pb_cuckoo_counts_enable(pb_cuckoo *c);
+int pb_cuckoo_counts_add_keys(pb_cuckoo *c, const pb_keys *keys);
+int pb_cuckoo_counts_add_fingerprints(pb_cuckoo *c, const uint32_t *fps, const uint32_t *amounts, uint64_t n, int on_device);
+int pb_cuckoo_counts_get_keys(pb_cuckoo *c, const pb_keys *keys, uint32_t *out, int out_on_device);
+int pb_cuckoo_counts_get_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, uint32_t *out);
+int pb_cuckoo_counts_set(pb_cuckoo *c, const uint32_t *fps, const uint32_t *vals, uint64_t n);
+int pb_cuckoo_counts_remove_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device, uint64_t *n_removed,
+                                 uint64_t *n_bins_removed);
+int pb_cuckoo_counts_remove_fingerprints(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint8_t *out,
+                                         uint64_t *n_removed, uint64_t *n_bins_removed);
+
 /* ---------------------------------------------------------------- roofline micro-benchmarks */
 /* n random RED.OR.b32 / atomicAdd.s32 over `words` 32-bit words with pre-generated uniform
  * indices and no hashing: the empirical random-atomic ceiling SURVEY 8(d) asks for. ms = device time. */

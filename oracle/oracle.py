@@ -416,6 +416,107 @@ class Cuckoo:
         return np.sort(out[:n])
 
 
+class CountingCuckoo:
+    """probables/cuckoo/countingcuckoo.py:156-210, :230-265 one key at a time (pure-Python loop over precomputed
+    fingerprints and bucket indices: small cases only).  Buckets are lists of [fingerprint, count]."""
+
+    def __init__(self, capacity: int, bucket_size: int = 4, max_swaps: int = 500, fp_bits: int = 32, rng_seed: int = 1):
+        import random
+
+        self.capacity, self.bucket_size, self.max_swaps, self.fp_bits = capacity, bucket_size, max_swaps, fp_bits
+        self.buckets: list[list[list[int]]] = [[] for _ in range(capacity)]
+        self.elements_added = 0  # _inserted_elements
+        self.unique_elements = 0
+        self._rng = random.Random(rng_seed)
+        self._info = Cuckoo(capacity, bucket_size, max_swaps, fp_bits)
+
+    def _indices(self, fp: int):  # cuckoo.py:483-490
+        return fp % self.capacity, fnv_1a(str(fp)) % self.capacity
+
+    def _find(self, i1: int, i2: int, fp: int):  # :267-273
+        for idx in (i1, i2):
+            for b in self.buckets[idx]:
+                if b[0] == fp:
+                    return b
+        return None
+
+    def _place(self, idx: int, fp: int, count: int) -> bool:  # :318-323
+        if len(self.buckets[idx]) < self.bucket_size:
+            self.buckets[idx].append([fp, count])
+            return True
+        return False
+
+    def _insert(self, fp: int, i1: int, i2: int):  # :230-265
+        if self._place(i1, fp, 1) or self._place(i2, fp, 1):
+            self.elements_added += 1
+            self.unique_elements += 1
+            return None
+        idx = self._rng.choice([i1, i2])
+        prv = [fp, 1]
+        for _ in range(self.max_swaps):
+            j = self._rng.randint(0, self.bucket_size - 1)
+            prv, self.buckets[idx][j] = self.buckets[idx][j], prv
+            a, b = self._indices(prv[0])
+            idx = b if idx == a else a
+            if self._place(idx, prv[0], prv[1]):
+                self.elements_added += 1
+                self.unique_elements += 1
+                return None
+        return prv
+
+    def add(self, keys: Keys) -> list:
+        """-> the homeless bins (empty when everything found a slot)"""
+        i1, i2, fp = self._info.fingerprint_info(keys)
+        homeless = []
+        for a, b, f in zip(i1.tolist(), i2.tolist(), fp.tolist()):
+            hit = self._find(a, b, f)  # :161-171
+            if hit is not None:
+                hit[1] += 1
+                self.elements_added += 1
+                continue
+            left = self._insert(f, a, b)
+            if left is not None:
+                homeless.append(left)
+        return homeless
+
+    def check(self, keys: Keys) -> np.ndarray:  # :175-191
+        i1, i2, fp = self._info.fingerprint_info(keys)
+        out = np.zeros(keys.n, dtype=np.uint32)
+        for n, (a, b, f) in enumerate(zip(i1.tolist(), i2.tolist(), fp.tolist())):
+            hit = self._find(a, b, f)
+            out[n] = hit[1] if hit is not None else 0
+        return out
+
+    def remove(self, keys: Keys) -> np.ndarray:  # :193-210
+        i1, i2, fp = self._info.fingerprint_info(keys)
+        out = np.zeros(keys.n, dtype=bool)
+        for n, (a, b, f) in enumerate(zip(i1.tolist(), i2.tolist(), fp.tolist())):
+            for idx in (a, b):
+                hit = next((x for x in self.buckets[idx] if x[0] == f), None)
+                if hit is not None:
+                    hit[1] -= 1
+                    self.elements_added -= 1
+                    if hit[1] == 0:
+                        self.buckets[idx].remove(hit)
+                        self.unique_elements -= 1
+                    out[n] = True
+                    break
+        return out
+
+    def bins(self) -> list:
+        return sorted((b[0], b[1]) for bucket in self.buckets for b in bucket)
+
+    def export(self) -> bytes:  # :216-228, :325-334
+        import struct
+
+        out = bytearray()
+        for bucket in self.buckets:
+            for b in bucket:
+                out += struct.pack("II", b[0], b[1])
+            out += b"\0" * (8 * (self.bucket_size - len(bucket)))
+        return bytes(out) + struct.pack("II", self.bucket_size, self.max_swaps)
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

@@ -2,7 +2,7 @@
 
 Same class names, constructor arguments, properties, exceptions and `hash_function` plugin seam as
 `probables` (barrust/pyprobables v0.7.0) for BloomFilter, CountingBloomFilter, Expanding/RotatingBloomFilter, CountMinSketch (+Mean, +MeanMin)
-and CuckooFilter, with the batch methods `add_many` / `check_many` added.  State lives in GPU memory; every
+CuckooFilter and CountingCuckooFilter, with the batch methods `add_many` / `check_many` added.  State lives in GPU memory; every
 add/check runs in hand-written sm_100a CUDA kernels behind the C ABI of include/pb200.h.
 There is no CPU fallback: without libpb200.so and a CUDA device the constructors raise.
 """
@@ -11,6 +11,7 @@ from . import hashes
 from ._native import Context, NativeError, NoDeviceError, build, default_context, device_count
 from .bloom import BloomFilter
 from .countingbloom import CountingBloomFilter
+from .countingcuckoo import CountingCuckooFilter
 from .countminsketch import CountMeanMinSketch, CountMeanSketch, CountMinSketch
 from .cuckoo import CuckooFilter
 from .expandingbloom import ExpandingBloomFilter, RotatingBloomFilter
@@ -37,6 +38,7 @@ __all__ = [
     "CountMeanSketch",
     "CountMeanMinSketch",
     "CuckooFilter",
+    "CountingCuckooFilter",
     "InitializationError",
     "NotSupportedError",
     "ProbablesBaseException",

@@ -175,6 +175,14 @@ SIGNATURES: dict[str, list] = {
     "pb_cuckoo_device_ptr": [_vp, _P(_vp), _P(_u64)],
     "pb_cuckoo_capacity": [_vp, _P(_u64)],
     "pb_cuckoo_expand": [_vp, _u64, _P(_u64), _vp, _u64],
+    "pb_cuckoo_counts_enable": [_vp],
+    "pb_cuckoo_counts_add_keys": [_vp, _KP],
+    "pb_cuckoo_counts_add_fingerprints": [_vp, _vp, _vp, _u64, _i32],
+    "pb_cuckoo_counts_get_keys": [_vp, _KP, _vp, _i32],
+    "pb_cuckoo_counts_get_fingerprints": [_vp, _vp, _u64, _vp],
+    "pb_cuckoo_counts_set": [_vp, _vp, _vp, _u64],
+    "pb_cuckoo_counts_remove_keys": [_vp, _KP, _vp, _i32, _P(_u64), _P(_u64)],
+    "pb_cuckoo_counts_remove_fingerprints": [_vp, _vp, _vp, _u64, _vp, _P(_u64), _P(_u64)],
     "pb_microbench_random_atomic": [_vp, _u64, _u64, _i32, _i32, _P(C.c_float)],
 }
 _SPECIAL = {"pb_version": (C.c_int, []), "pb_last_error": (_cp, [])}

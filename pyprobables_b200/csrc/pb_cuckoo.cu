@@ -45,6 +45,10 @@ struct pb_cuckoo {
     uint32_t *zero_flag = nullptr;  // device word: 1 when fingerprint 0 is stored
     uint64_t *alt = nullptr;        // pre-indexed mode: idx_2 per slot (allocated by the first pre-indexed call)
     FastMod fm;
+    // CountingCuckooFilter (pb_cuckoo_counts_*): fingerprint -> count, open addressing, entry `cap` = fingerprint 0
+    uint32_t *cnt_keys = nullptr, *cnt_vals = nullptr, *cnt_tickets = nullptr;
+    uint64_t cnt_cap = 0;   // power of two (entries 0..cap-1 hashed, entry cap for fingerprint 0)
+    uint64_t cnt_used = 0;  // keys ever claimed (entries whose count fell to 0 stay claimed until the next rebuild)
 };
 
 namespace pb {
@@ -501,6 +505,114 @@ __global__ void __launch_bounds__(256) count_nonzero_kernel(const uint32_t *__re
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// ---- CountingCuckooFilter (cuckoo/countingcuckoo.py:156-210) -------------------------------------------------------
+// The reference keeps (fingerprint, count) bins; add() of a fingerprint that is already stored bumps its count (:165-171),
+// otherwise the fingerprint goes in with count 1 (:172, :230-265) and the count travels with it through evictions.  A
+// fingerprint is therefore stored at most once, and the counts are a function fingerprint -> count that no eviction
+// touches: they live in their own open-addressing map next to the (unchanged) fingerprint table.  add = the set insert
+// above + one atomicAdd per key here; check = one map lookup; remove = decrement, and take the fingerprint out of the
+// table when its count reaches 0 (:193-210).
+struct FpCounts {
+    uint32_t *keys, *vals, *tickets;
+    uint64_t mask;  // cap - 1; index cap = fingerprint 0
+};
+
+__device__ __forceinline__ uint64_t counts_claim(const FpCounts &m, uint32_t fp, unsigned long long *used) {
+    if (fp == 0u) return m.mask + 1;
+    uint64_t s = sm64((uint64_t)fp) & m.mask;
+    for (;;) {
+        const uint32_t old = atomicCAS(m.keys + s, 0u, fp);
+        if (old == 0u) {
+            atomicAdd(used, 1ull);
+            return s;
+        }
+        if (old == fp) return s;
+        s = (s + 1) & m.mask;
+    }
+}
+// index of fp's entry, or ~0 when the map never saw it
+__device__ __forceinline__ uint64_t counts_find(const FpCounts &m, uint32_t fp) {
+    if (fp == 0u) return m.mask + 1;
+    uint64_t s = sm64((uint64_t)fp) & m.mask;
+    for (;;) {
+        const uint32_t k = __ldcg(m.keys + s);
+        if (k == fp) return s;
+        if (k == 0u) return ~0ull;
+        s = (s + 1) & m.mask;
+    }
+}
+
+// (fps may hold 32-bit hashes still to be cut to fp_bits, as in the set kernels above: the cut is idempotent)
+__global__ void __launch_bounds__(256) counts_add_kernel(const uint32_t *__restrict__ fps, const uint32_t *__restrict__ amounts, uint64_t n,
+                                                         uint32_t fp_bits, FpCounts m, unsigned long long *used) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], fp_bits);
+        atomicAdd(m.vals + counts_claim(m, fp, used), amounts ? amounts[i] : 1u);  // :165-171 / :230-241
+    }
+}
+__global__ void __launch_bounds__(256) counts_get_kernel(const uint32_t *__restrict__ fps, uint64_t n, uint32_t fp_bits, FpCounts m,
+                                                         uint32_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = counts_find(m, cuckoo_fingerprint((uint64_t)fps[i], fp_bits));
+        out[i] = s == ~0ull ? 0u : __ldcg(m.vals + s);  // :175-191
+    }
+}
+__global__ void __launch_bounds__(256) counts_set_kernel(const uint32_t *__restrict__ fps, const uint32_t *__restrict__ vals, uint64_t n,
+                                                         FpCounts m, unsigned long long *used) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m.vals[counts_claim(m, fps[i], used)] = vals ? vals[i] : 0u;
+}
+// remove, pass 1: every occurrence of a stored fingerprint draws a ticket; tickets below the count are the removals
+// that succeed (:199-208: a key removed more often than it was added runs dry).  The counts do not move in this pass.
+__global__ void __launch_bounds__(256) counts_remove_tickets(const uint32_t *__restrict__ fps, uint64_t n, uint32_t fp_bits, FpCounts m,
+                                                             uint32_t *__restrict__ ticket_of, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = counts_find(m, cuckoo_fingerprint((uint64_t)fps[i], fp_bits));
+        uint32_t t = 0xFFFFFFFFu, have = 0;
+        if (s != ~0ull && (have = __ldcg(m.vals + s)) != 0u) t = atomicAdd(m.tickets + s, 1u);
+        ticket_of[i] = t;
+        out[i] = (uint8_t)(t < have);
+    }
+}
+// pass 2: the holder of ticket 0 settles its fingerprint: count -= min(tickets, count); a count of 0 takes the
+// fingerprint out of the table (:205-207)
+template <int BS>
+__global__ void __launch_bounds__(256) counts_remove_settle(const uint32_t *__restrict__ fps, const uint64_t *__restrict__ i2_in, uint64_t n,
+                                                            CuckooDev c, FpCounts m, const uint32_t *__restrict__ ticket_of,
+                                                            unsigned long long *totals /* [0] removed, [1] bins removed */) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (ticket_of[i] != 0u) continue;
+        const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits);
+        const uint64_t s = counts_find(m, fp);
+        const uint32_t drawn = m.tickets[s], have = m.vals[s];
+        const uint32_t dec = drawn < have ? drawn : have;
+        m.vals[s] = have - dec;
+        m.tickets[s] = 0u;
+        atomicAdd(totals, (unsigned long long)dec);
+        if (have == dec) {
+            bool hit;
+            if (fp == 0u) {
+                hit = atomicExch(c.zero_flag, 0u) != 0u;
+            } else {
+                uint64_t i1, i2;
+                cuckoo_buckets(c, fp, i1, i2);
+                if (i2_in) i2 = i2_in[i];
+                hit = bucket_take<BS>(c, i1, fp) || bucket_take<BS>(c, i2, fp);
+            }
+            if (hit) atomicAdd(totals + 1, 1ull);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) counts_rehash_kernel(FpCounts from, FpCounts to, unsigned long long *used) {
+    const uint64_t n = from.mask + 2;  // incl. the entry of fingerprint 0
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = from.vals[i];
+        if (v == 0u) continue;
+        if (i == from.mask + 1) to.vals[to.mask + 1] = v;
+        else to.vals[counts_claim(to, from.keys[i], used)] = v;
+    }
+}
+
 // ---------------------------------------------------------------- host side
 static CuckooDev dev_view(const pb_cuckoo *c) {
     CuckooDev d;
@@ -535,7 +647,7 @@ static int ensure_claim(pb_cuckoo *c, uint32_t **bitmap, uint64_t *bytes) {
     return PB_OK;
 }
 
-// scratch layout inside ctx->small: [0] popcount, [8] stray, [16..17] cms sums, [32..35] CuckooCounters
+// scratch layout inside ctx->small: [0] popcount, [8] stray, [16..17] cms sums, [32..35] CuckooCounters, [44..46] count map
 static CuckooCounters *counters_dev(pb_ctx *ctx) { return (CuckooCounters *)((unsigned long long *)ctx->small.p + 32); }
 
 struct CuckooResult {
@@ -773,6 +885,9 @@ int pb_cuckoo_destroy(pb_cuckoo *c) {
     cudaFree(c->slots);
     cudaFree(c->zero_flag);
     if (c->alt) cudaFree(c->alt);
+    cudaFree(c->cnt_keys);
+    cudaFree(c->cnt_vals);
+    cudaFree(c->cnt_tickets);
     delete c;
     return PB_OK;
 }
@@ -782,6 +897,11 @@ int pb_cuckoo_clear(pb_cuckoo *c) {
     DeviceGuard g(c->ctx->device);
     PB_CUDA(cudaMemsetAsync(c->slots, 0, ((c->nslots + 3) & ~(uint64_t)3) * 4, c->ctx->stream));
     PB_CUDA(cudaMemsetAsync(c->zero_flag, 0, 4, c->ctx->stream));
+    if (c->cnt_cap) {
+        PB_CUDA(cudaMemsetAsync(c->cnt_keys, 0, (c->cnt_cap + 1) * 4, c->ctx->stream));
+        PB_CUDA(cudaMemsetAsync(c->cnt_vals, 0, (c->cnt_cap + 1) * 4, c->ctx->stream));
+        c->cnt_used = 0;
+    }
     return PB_OK;
 }
 
@@ -1159,6 +1279,300 @@ int pb_cuckoo_expand(pb_cuckoo *c, uint64_t new_capacity, uint64_t *n_failed, ui
         set_error("The CuckooFilter failed to expand (%llu fingerprints left homeless)", (unsigned long long)h->n_failed);
         return PB_ERR_CUCKOO_FULL;
     }
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------- CountingCuckooFilter: the fingerprint -> count map
+static FpCounts counts_view(const pb_cuckoo *c) {
+    FpCounts m;
+    m.keys = c->cnt_keys;
+    m.vals = c->cnt_vals;
+    m.tickets = c->cnt_tickets;
+    m.mask = c->cnt_cap - 1;
+    return m;
+}
+
+static unsigned long long *counts_scratch(pb_ctx *ctx) { return (unsigned long long *)ctx->small.p + 44; }  // [44..46]
+
+// (re)builds the map with `cap` hashed entries, carrying over every non-zero count
+static int counts_rebuild(pb_cuckoo *c, uint64_t cap) {
+    pb_ctx *ctx = c->ctx;
+    uint32_t *k = nullptr, *v = nullptr, *t = nullptr;
+    const size_t bytes = (size_t)(cap + 1) * 4;
+    if (cudaMalloc(&k, bytes) != cudaSuccess || cudaMalloc(&v, bytes) != cudaSuccess || cudaMalloc(&t, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(k), cudaFree(v), cudaFree(t);
+        set_error("cudaMalloc of the %llu-entry count map failed", (unsigned long long)cap);
+        return PB_ERR_OOM;
+    }
+    PB_CUDA(cudaMemsetAsync(k, 0, bytes, ctx->stream));
+    PB_CUDA(cudaMemsetAsync(v, 0, bytes, ctx->stream));
+    PB_CUDA(cudaMemsetAsync(t, 0, bytes, ctx->stream));
+    uint64_t used = 0;
+    if (c->cnt_cap) {
+        PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+        unsigned long long *acc = counts_scratch(ctx);
+        PB_CUDA(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+        FpCounts to;
+        to.keys = k, to.vals = v, to.tickets = t, to.mask = cap - 1;
+        launch_begin(ctx);
+        counts_rehash_kernel<<<grid_for(ctx, c->cnt_cap + 1, 256, 8), 256, 0, ctx->stream>>>(counts_view(c), to, acc);
+        PB_TRY(check_launch(ctx, "cuckoo_counts_rehash"));
+        PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        used = *(uint64_t *)ctx->pinned_small;
+        cudaFree(c->cnt_keys), cudaFree(c->cnt_vals), cudaFree(c->cnt_tickets);
+    }
+    c->cnt_keys = k, c->cnt_vals = v, c->cnt_tickets = t;
+    c->cnt_cap = cap;
+    c->cnt_used = used;
+    return PB_OK;
+}
+
+static uint64_t counts_cap_for(uint64_t entries) {
+    uint64_t cap = 1024;
+    while (cap < entries * 2) cap <<= 1;
+    return cap;
+}
+
+// room for `incoming` more distinct fingerprints at a load of at most 3/4 (probe sequences stay short and end)
+static int counts_reserve(pb_cuckoo *c, uint64_t incoming) {
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
+    if ((c->cnt_used + incoming) * 4 <= c->cnt_cap * 3) return PB_OK;
+    PB_TRY(counts_rebuild(c, c->cnt_cap));  // drops the entries whose count is 0
+    if ((c->cnt_used + incoming) * 4 <= c->cnt_cap * 3) return PB_OK;
+    return counts_rebuild(c, counts_cap_for(c->cnt_used + incoming));
+}
+
+static int chunk_fps(pb_ctx *ctx, pb_cuckoo *c, const DevKeys &dk, int slot, uint32_t **out) {
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[slot], dk.n * 8));
+    uint32_t *fps = (uint32_t *)ctx->aux_stage[slot].p;  // [fps n][tickets n]
+    launch_begin(ctx);
+    if (is_fixed16(dk)) {
+        cuckoo_fp_fixed16<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)dk.data, dk.n, c->fp_bits, fps);
+    } else {
+        const uint64_t tiles = (dk.n + kTileKeys - 1) / kTileKeys;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 4);
+        if (dk.sym_width == 4) cuckoo_fp_staged<4><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+        else cuckoo_fp_staged<1><<<grid, kTileKeys, 0, ctx->stream>>>(dk, c->fp_bits, fps);
+    }
+    *out = fps;
+    return check_launch(ctx, "cuckoo_fp");
+}
+
+static int counts_sync_used(pb_cuckoo *c, unsigned long long *acc) {
+    pb_ctx *ctx = c->ctx;
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, acc, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    c->cnt_used += ((uint64_t *)ctx->pinned_small)[0];
+    return PB_OK;
+}
+
+// Turns the filter into a counting one (or re-fits the map after pb_cuckoo_expand / pb_cuckoo_resize).
+int pb_cuckoo_counts_enable(pb_cuckoo *c) {
+    PB_REQUIRE(c, "handle is NULL");
+    DeviceGuard g(c->ctx->device);
+    const uint64_t want = counts_cap_for(c->nslots + 1);
+    if (c->cnt_cap >= want) return PB_OK;
+    return counts_rebuild(c, want);
+}
+
+struct CountsArgs {
+    pb_cuckoo *c;
+    unsigned long long *acc;
+    uint32_t *out_dev, *out_host;
+    uint8_t *flag_dev, *flag_host;
+};
+
+// CountingCuckooFilter.add, the counting half: count[fp(key)] += 1 for every key (the set half is pb_cuckoo_add_keys)
+int pb_cuckoo_counts_add_keys(pb_cuckoo *c, const pb_keys *keys) {
+    PB_REQUIRE(c && keys, "NULL argument");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    if (keys->n == 0) return validate_keys(keys);
+    PB_TRY(counts_reserve(c, keys->n));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = counts_scratch(ctx);
+    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+    CountsArgs a{c, acc, nullptr, nullptr, nullptr, nullptr};
+    auto fn = [](pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) -> int {
+        (void)first;
+        CountsArgs *a = (CountsArgs *)user;
+        uint32_t *fps;
+        PB_TRY(chunk_fps(ctx, a->c, dk, slot, &fps));
+        launch_begin(ctx);
+        counts_add_kernel<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>(fps, nullptr, dk.n, a->c->fp_bits, counts_view(a->c), a->acc);
+        return check_launch(ctx, "cuckoo_counts_add");
+    };
+    PB_TRY(for_each_chunk(ctx, keys, fn, &a, 1ull << 28));
+    return counts_sync_used(c, acc);
+}
+
+// count[fp] += amounts[i] (NULL: 1) for host or device arrays of fingerprints (plugin hash path, load)
+int pb_cuckoo_counts_add_fingerprints(pb_cuckoo *c, const uint32_t *fps, const uint32_t *amounts, uint64_t n, int on_device) {
+    PB_REQUIRE(c && (fps || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(counts_reserve(c, n));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = counts_scratch(ctx);
+    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+    const uint32_t *d_fps = fps, *d_amt = amounts;
+    if (!on_device) {
+        PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 8));
+        uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
+        PB_CUDA(cudaMemcpyAsync(d, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_fps = d;
+        if (amounts) {
+            PB_CUDA(cudaMemcpyAsync(d + n, amounts, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d_amt = d + n;
+        }
+    }
+    launch_begin(ctx);
+    counts_add_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_fps, d_amt, n, c->fp_bits, counts_view(c), acc);
+    PB_TRY(check_launch(ctx, "cuckoo_counts_add"));
+    return counts_sync_used(c, acc);
+}
+
+// CountingCuckooFilter.check (:175-191): the stored count of every key's fingerprint, 0 when it is not stored
+int pb_cuckoo_counts_get_keys(pb_cuckoo *c, const pb_keys *keys, uint32_t *out, int out_on_device) {
+    PB_REQUIRE(c && keys && (out || keys->n == 0), "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
+    PB_REQUIRE(keys->on_device || !out_on_device, "device output needs device keys");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    CountsArgs a{c, nullptr, out_on_device ? out : nullptr, out_on_device ? nullptr : out, nullptr, nullptr};
+    auto fn = [](pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) -> int {
+        CountsArgs *a = (CountsArgs *)user;
+        uint32_t *fps;
+        PB_TRY(chunk_fps(ctx, a->c, dk, slot, &fps));
+        uint32_t *o = a->out_dev ? a->out_dev + first : nullptr;
+        if (!o) {
+            PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n * 4));
+            o = (uint32_t *)ctx->out_stage[slot].p;
+        }
+        launch_begin(ctx);
+        counts_get_kernel<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>(fps, dk.n, a->c->fp_bits, counts_view(a->c), o);
+        PB_TRY(check_launch(ctx, "cuckoo_counts_get"));
+        if (a->out_host) PB_CUDA(cudaMemcpyAsync(a->out_host + first, o, dk.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        return PB_OK;
+    };
+    return for_each_chunk(ctx, keys, fn, &a, 1ull << 28);
+}
+
+// the same for host arrays of fingerprints (export: the count next to every stored fingerprint; plugin hash path)
+int pb_cuckoo_counts_get_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_t n, uint32_t *out) {
+    PB_REQUIRE(c && ((fps && out) || n == 0), "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 8));
+    uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
+    PB_CUDA(cudaMemcpyAsync(d, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    launch_begin(ctx);
+    counts_get_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d, n, c->fp_bits, counts_view(c), d + n);
+    PB_TRY(check_launch(ctx, "cuckoo_counts_get"));
+    PB_CUDA(cudaMemcpyAsync(out, d + n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+// count[fp] = vals[i] (NULL: 0) for host arrays: load (:286-303), and forgetting fingerprints that were given up as
+// homeless (:264-265 hands the bin back to the caller, who raises)
+int pb_cuckoo_counts_set(pb_cuckoo *c, const uint32_t *fps, const uint32_t *vals, uint64_t n) {
+    PB_REQUIRE(c && (fps || n == 0), "NULL argument");
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(counts_reserve(c, n));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = counts_scratch(ctx);
+    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 8));
+    uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
+    PB_CUDA(cudaMemcpyAsync(d, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (vals) PB_CUDA(cudaMemcpyAsync(d + n, vals, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    launch_begin(ctx);
+    counts_set_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d, vals ? d + n : nullptr, n, counts_view(c), acc);
+    PB_TRY(check_launch(ctx, "cuckoo_counts_set"));
+    return counts_sync_used(c, acc);
+}
+
+static int counts_remove_device(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint32_t *tickets, uint8_t *out,
+                                unsigned long long *acc) {
+    pb_ctx *ctx = c->ctx;
+    launch_begin(ctx);
+    counts_remove_tickets<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(fps, n, c->fp_bits, counts_view(c), tickets, out);
+    PB_TRY(check_launch(ctx, "cuckoo_counts_remove_tickets"));
+    const CuckooDev cd = dev_view(c);
+    PB_BS_DISPATCH(c, counts_remove_settle, grid_for(ctx, n, 256, 8), 256, fps, i2, n, cd, counts_view(c), tickets, acc + 1);
+    return check_launch(ctx, "cuckoo_counts_remove_settle");
+}
+
+// CountingCuckooFilter.remove (:193-210) for every key: out[i] = 1 when a stored count was decremented.  A key that
+// occurs more often in the batch than its count reports 1 exactly `count` times.  n_removed = decrements,
+// n_bins_removed = fingerprints whose count reached 0 and that left the table.
+int pb_cuckoo_counts_remove_keys(pb_cuckoo *c, const pb_keys *keys, uint8_t *out, int out_on_device, uint64_t *n_removed,
+                                 uint64_t *n_bins_removed) {
+    PB_REQUIRE(c && keys && n_removed && n_bins_removed && (out || keys->n == 0), "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
+    PB_REQUIRE(keys->on_device || !out_on_device, "device output needs device keys");
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    *n_removed = *n_bins_removed = 0;
+    if (keys->n == 0) return validate_keys(keys);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = counts_scratch(ctx);
+    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+    CountsArgs a{c, acc, nullptr, nullptr, out_on_device ? out : nullptr, out_on_device ? nullptr : out};
+    auto fn = [](pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) -> int {
+        CountsArgs *a = (CountsArgs *)user;
+        uint32_t *fps;
+        PB_TRY(chunk_fps(ctx, a->c, dk, slot, &fps));
+        uint8_t *o = a->flag_dev ? a->flag_dev + first : nullptr;
+        if (!o) {
+            PB_TRY(scratch_reserve(ctx, ctx->out_stage[slot], dk.n));
+            o = (uint8_t *)ctx->out_stage[slot].p;
+        }
+        PB_TRY(counts_remove_device(a->c, fps, nullptr, dk.n, fps + dk.n, o, a->acc));
+        if (a->flag_host) PB_CUDA(cudaMemcpyAsync(a->flag_host + first, o, dk.n, cudaMemcpyDeviceToHost, ctx->stream));
+        return PB_OK;
+    };
+    PB_TRY(for_each_chunk(ctx, keys, fn, &a, 1ull << 28));
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, acc, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_removed = ((uint64_t *)ctx->pinned_small)[1];
+    *n_bins_removed = ((uint64_t *)ctx->pinned_small)[2];
+    return PB_OK;
+}
+
+// the same for host arrays of fingerprints; i2 (may be NULL) = the caller's idx_2 of every fingerprint (custom hash_function)
+int pb_cuckoo_counts_remove_fingerprints(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint8_t *out,
+                                         uint64_t *n_removed, uint64_t *n_bins_removed) {
+    PB_REQUIRE(c && n_removed && n_bins_removed && ((fps && out) || n == 0), "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
+    *n_removed = *n_bins_removed = 0;
+    if (n == 0) return PB_OK;
+    pb_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *acc = counts_scratch(ctx);
+    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 8));
+    PB_TRY(scratch_reserve(ctx, ctx->out_stage[0], n * 9));
+    uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
+    uint64_t *d_i2 = i2 ? (uint64_t *)ctx->out_stage[0].p : nullptr;
+    uint8_t *d_out = (uint8_t *)ctx->out_stage[0].p + n * 8;
+    PB_CUDA(cudaMemcpyAsync(d, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (i2) PB_CUDA(cudaMemcpyAsync(d_i2, i2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PB_TRY(counts_remove_device(c, d, d_i2, n, d + n, d_out, acc));
+    PB_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, acc, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_removed = ((uint64_t *)ctx->pinned_small)[1];
+    *n_bins_removed = ((uint64_t *)ctx->pinned_small)[2];
     return PB_OK;
 }
 

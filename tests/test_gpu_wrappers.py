@@ -186,3 +186,96 @@ def test_rotating_batch_equals_one_at_a_time(pb, orc, queue):
     assert stack_state(r) == oracle_state(o)
     r.add_many(keys[25_000:]), o.add(orc.pack(keys[25_000:]))
     assert stack_state(r) == oracle_state(o)
+
+
+# ---------------------------------------------------------------- CountingCuckooFilter (cuckoo/countingcuckoo.py)
+def test_counting_cuckoo_vs_reference(pb, orc, golden):
+    g = golden["ccf"]
+    keys = orc.uniform_keys(0, 1300)
+    f = pb.CountingCuckooFilter(capacity=g["capacity"], bucket_size=g["bucket_size"], max_swaps=g["max_swaps"], auto_expand=False)
+    f.add_many(keys[g["draws"]])
+    assert f.bins() == [tuple(x) for x in g["bins"]]
+    assert (f.elements_added, f.unique_elements) == (g["elements_added"], g["unique_elements"])
+    assert f.load_factor() == g["load_factor"]
+    assert f.check_many(keys).tolist() == g["check_0_1300"]
+    assert f.remove_many(keys[0:1300:3]).tolist() == g["removed_step3"]
+    assert f.bins() == [tuple(x) for x in g["bins_after_remove"]]
+    assert (f.elements_added, f.unique_elements) == (g["elements_added_after_remove"], g["unique_after_remove"])
+    # wire format round trip
+    back = pb.CountingCuckooFilter.frombytes(bytes(f))
+    assert back.bins() == f.bins() and back.capacity == f.capacity
+    assert (back.elements_added, back.unique_elements) == (f.elements_added, f.unique_elements)
+    assert (back.check_many(keys) == f.check_many(keys)).all()
+
+
+def test_counting_cuckoo_reference_literals(pb, golden):
+    # tests/countingcuckoo_test.py style: single adds, counts, contains, remove down to zero
+    f = pb.CountingCuckooFilter(capacity=100, max_swaps=5)
+    for w, n in (("this is a test", 3), ("this is another test", 1)):
+        for _ in range(n):
+            f.add(w)
+    assert f.check("this is a test") == 3 and f.check("this is another test") == 1 and f.check("nope") == 0
+    assert "this is a test" in f and "nope" not in f
+    assert f.elements_added == 4 and f.unique_elements == 2
+    assert f.remove("this is a test") and f.check("this is a test") == 2 and f.elements_added == 3 and f.unique_elements == 2
+    assert f.remove("this is another test") and f.check("this is another test") == 0 and f.unique_elements == 1
+    assert not f.remove("this is another test") and not f.remove("nope") and f.elements_added == 2
+    b = f.buckets
+    assert sum(len(x) for x in b) == 1 and [x for x in b if x][0][0].count == 2
+    # export bytes where no eviction happens (slot order = first insertion order), inserted in key order
+    e = golden["ccf_export"]
+    ctx = pb.default_context()
+    ctx.set_option("cuckoo_serial", 1)
+    try:
+        s = pb.CountingCuckooFilter(capacity=e["capacity"], bucket_size=4, max_swaps=5)
+        s.add_many([str(i % 400) for i in range(600)])
+    finally:
+        ctx.set_option("cuckoo_serial", 0)
+    assert len(bytes(s)) == e["export_len"] and md5(bytes(s)) == e["export_md5"]
+    assert (s.elements_added, s.unique_elements) == (e["elements_added"], e["unique_elements"])
+
+
+def test_counting_cuckoo_batch_equals_one_at_a_time(pb, orc):
+    """a skewed stream at high load: many repeats inside one batch, evictions, removals that run counts dry"""
+    rng = np.random.default_rng(5)
+    pool = orc.uniform_keys(900_000, 60_000)
+    draws = np.minimum(rng.zipf(1.3, 150_000) - 1, 59_999)
+    stream = pool[draws]
+    cap = 1 << 14  # 65 536 slots; ~29 000 distinct keys
+    f = pb.CountingCuckooFilter(capacity=cap, bucket_size=4, max_swaps=500, auto_expand=False)
+    o = orc.CountingCuckoo(cap, 4, 500)
+    f.add_many(stream[:100_000]), o.add(orc.pack(stream[:100_000]))
+    f.add_many(stream[100_000:]), o.add(orc.pack(stream[100_000:]))
+    assert f.bins() == o.bins() and (f.elements_added, f.unique_elements) == (o.elements_added, o.unique_elements)
+    probes = np.concatenate([pool[:5000], orc.uniform_keys(5_000_000, 5000)])
+    assert (f.check_many(probes) == o.check(orc.pack(probes))).all()
+    rem = pool[np.minimum(rng.zipf(1.3, 40_000) - 1, 59_999)]  # popular keys are removed more often than they were added
+    got, want = f.remove_many(rem), o.remove(orc.pack(rem))
+    assert (got == want).all()
+    assert f.bins() == o.bins() and (f.elements_added, f.unique_elements) == (o.elements_added, o.unique_elements)
+    assert (f.check_many(probes) == o.check(orc.pack(probes))).all()
+
+
+def test_counting_cuckoo_expand_full_and_plugin_hash(pb, orc):
+    keys = orc.uniform_keys(0, 3000)
+    f = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=20)  # auto_expand: 200 slots -> grows
+    f.add_many(np.concatenate([keys, keys[:1000]]))
+    assert f.capacity > 100 and f.unique_elements == 3000 and f.elements_added == 4000
+    c = f.check_many(keys)
+    assert (c[:1000] == 2).all() and (c[1000:] == 1).all()
+    full = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=20, auto_expand=False)
+    with pytest.raises(pb.CuckooFilterFullError):
+        full.add_many(keys)
+    assert full.unique_elements == len(full.bins()) <= 200 and full.elements_added == sum(c for _, c in full.bins())
+
+    def md5_int(key):
+        if isinstance(key, str):
+            key = key.encode("utf-8")
+        return int.from_bytes(hashlib.md5(key).digest()[:8], "big")
+
+    words = [f"w{i % 700}" for i in range(2000)]
+    p = pb.CountingCuckooFilter(capacity=400, bucket_size=4, max_swaps=100, hash_function=md5_int)
+    p.add_many(words)
+    assert p.unique_elements == 700 and p.elements_added == 2000
+    assert p.check("w5") == 3 and p.check("w699") == 2 and p.check("zzz") == 0
+    assert p.remove("w699") and p.remove("w699") and not p.remove("w699") and p.unique_elements == 699

@@ -51,3 +51,20 @@ def test_rotating_stream(orc, golden):
     assert stack_state(o) == g["after_pop"]
     o.add(orc.pack(orc.uniform_keys(6000, 500)), force=True)
     assert stack_state(o) == g["after_force_500"]
+
+
+def test_counting_cuckoo_vs_reference(orc, golden):
+    g = golden["ccf"]
+    keys = orc.uniform_keys(0, 1300)
+    o = orc.CountingCuckoo(g["capacity"], g["bucket_size"], g["max_swaps"])
+    assert o.add(orc.pack(keys[g["draws"]])) == []
+    assert o.bins() == [tuple(x) for x in g["bins"]]  # whatever victims the eviction walk picked
+    assert (o.elements_added, o.unique_elements) == (g["elements_added"], g["unique_elements"])
+    assert o.check(orc.pack(keys)).tolist() == g["check_0_1300"]
+    assert o.remove(orc.pack(keys[0:1300:3])).tolist() == g["removed_step3"]
+    assert o.bins() == [tuple(x) for x in g["bins_after_remove"]]
+    assert (o.elements_added, o.unique_elements) == (g["elements_added_after_remove"], g["unique_after_remove"])
+    e = golden["ccf_export"]
+    o = orc.CountingCuckoo(e["capacity"], 4, 5)
+    o.add(orc.pack([str(i % 400) for i in range(600)]))
+    assert md5(o.export()) == e["export_md5"] and len(o.export()) == e["export_len"]
