@@ -367,6 +367,45 @@ class CMS:
         return out
 
 
+class HeavyHitters(CMS):
+    """countminsketch.py:617-661: the dictionary bookkeeping, one key at a time, over the sketch's per-key return values"""
+
+    def __init__(self, num_hitters: int, width: int, depth: int):
+        super().__init__(width, depth)
+        self.num_hitters, self.top_x, self.top_x_size, self.smallest = num_hitters, {}, 0, 0
+
+    def add_tracked(self, names: list, keys: Keys, num_els=1) -> np.ndarray:
+        rets = self.add(keys, num_els, want_returns=True)
+        for key, res in zip(names, rets.tolist()):
+            if self.top_x_size < self.num_hitters:  # :645-649
+                tmp = self.top_x.get(key)
+                self.top_x[key] = res
+                if tmp is None:
+                    self.top_x_size = len(self.top_x)
+            elif key in self.top_x:  # :650-651
+                self.top_x[key] = res
+            elif res > self.smallest:  # :652-659
+                self.top_x[key] = res
+                self.top_x.pop(min(self.top_x, key=self.top_x.get), None)
+                self.smallest = self.top_x[min(self.top_x, key=self.top_x.get)]
+        return rets
+
+
+class StreamThreshold(CMS):
+    """countminsketch.py:787-803"""
+
+    def __init__(self, threshold: int, width: int, depth: int):
+        super().__init__(width, depth)
+        self.threshold, self.meets = threshold, {}
+
+    def add_tracked(self, names: list, keys: Keys, num_els=1) -> np.ndarray:
+        rets = self.add(keys, num_els, want_returns=True)
+        for key, res in zip(names, rets.tolist()):
+            if res >= self.threshold:
+                self.meets[key] = res
+        return rets
+
+
 class Cuckoo:
     """probables/cuckoo/cuckoo.py:291-315, :361-392, :440-453, :483-506"""
 

@@ -12,7 +12,7 @@ from ._native import Context, NativeError, NoDeviceError, build, default_context
 from .bloom import BloomFilter
 from .countingbloom import CountingBloomFilter
 from .countingcuckoo import CountingCuckooFilter
-from .countminsketch import CountMeanMinSketch, CountMeanSketch, CountMinSketch
+from .countminsketch import CountMeanMinSketch, CountMeanSketch, CountMinSketch, HeavyHitters, StreamThreshold
 from .cuckoo import CuckooFilter
 from .expandingbloom import ExpandingBloomFilter, RotatingBloomFilter
 from .exceptions import (
@@ -37,6 +37,8 @@ __all__ = [
     "CountMinSketch",
     "CountMeanSketch",
     "CountMeanMinSketch",
+    "HeavyHitters",
+    "StreamThreshold",
     "CuckooFilter",
     "CountingCuckooFilter",
     "InitializationError",

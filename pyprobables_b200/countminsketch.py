@@ -27,11 +27,13 @@ from . import _native
 from ._limits import INT64_T_MAX, INT64_T_MIN
 from .exceptions import CountMinSketchError, InitializationError, NotSupportedError
 from .hashes import default_fnv_1a, is_default_hash
-from .keys import pack_keys
+from .keys import device_batch, pack_keys
 
 _FOOTER = struct.Struct("IIq")  # width, depth, elements_added (countminsketch.py:122)
 _U64_MASK = (1 << 64) - 1
 _QUERY_CODE = {"min": 0, "mean": 1, "mean-min": 2}
+INT32_T_MAX = (1 << 31) - 1
+_RETURNS_CHUNK = 1 << 23  # keys per sort pass of add_many_returns
 
 
 class CountMinSketch:
@@ -230,6 +232,90 @@ class CountMinSketch:
             C.byref(ea),
         )
 
+    # ------------------------------------------------------------------ ordered batches: what add() returns for every key
+    def add_many_returns(self, keys, num_els=1):
+        """`[self.add(k, n) for k in keys]` as one batch -> int64 CUDA tensor [n]: the estimate right after each key's own
+        insertion (:267-288), earlier keys of the batch included.  The table ends up as after add_many.
+
+        A counter's value after key i is its old value plus the num_els of all keys up to i that fall on it (saturating
+        at INT32_MAX, which commutes with a running sum of non-negative amounts): per row a stable sort of the batch by
+        counter and a segmented running sum give that value for every key at once (torch.sort / cumsum on the
+        context's stream; the counter updates themselves are the add kernels of pb_cms.cu)."""
+        import torch
+
+        stream = torch.cuda.ExternalStream(self._ctx.stream, device=f"cuda:{self._ctx.device}")
+        dev = f"cuda:{self._ctx.device}"
+        d, w = self._depth, self._width
+        if self._fused:
+            kb = pack_keys(keys)
+            n = kb.n
+            dkb = device_batch(kb, self._ctx.device)
+        else:
+            if isinstance(keys, (str, bytes, bytearray, memoryview)):
+                keys = [keys]
+            h = self._hash_rows(keys)
+            n = h.shape[0]
+        scalar = isinstance(num_els, (int, np.integer))
+        if scalar:
+            if num_els < 0:
+                raise NotSupportedError("add_many_returns takes non-negative num_els (removals are not order-free)")
+        else:
+            num_els = np.ascontiguousarray(num_els, dtype=np.int64)
+            if num_els.shape != (n,):
+                raise ValueError("num_els must be an int or one int per key")
+            if n and num_els.min() < 0:
+                raise NotSupportedError("add_many_returns takes non-negative num_els (removals are not order-free)")
+        from .sharded import device_view
+
+        with torch.cuda.stream(stream):
+            out = torch.empty(n, dtype=torch.int64, device=dev)
+            if n == 0:
+                return out
+            table = device_view(self.device_ptr(), d * w, "<i4", self._ctx.device)
+            if self._fused:
+                idx = torch.empty((n, d), dtype=torch.int64, device=dev)
+                _native.call("pb_bloom_index_keys", self._ctx.handle, dkb.ref(), w, d, C.c_void_p(idx.data_ptr()))
+            else:
+                idx = torch.from_numpy((h % np.uint64(w)).view(np.int64)).to(dev)
+            amounts = None if scalar else torch.from_numpy(num_els).to(dev)
+            ea = max(INT64_T_MIN, min(INT64_T_MAX, self._elements_added))
+            for lo in range(0, n, _RETURNS_CHUNK):
+                hi = min(lo + _RETURNS_CHUNK, n)
+                cn = hi - lo
+                wv = torch.full((cn,), int(num_els), dtype=torch.int64, device=dev) if scalar else amounts[lo:hi]
+                ar = torch.arange(cn, device=dev)
+                vals = torch.empty((cn, d), dtype=torch.int64, device=dev)
+                for r in range(d):
+                    cs, order = torch.sort(idx[lo:hi, r], stable=True)
+                    ws = wv[order]
+                    csum = torch.cumsum(ws, 0)
+                    start = torch.ones(cn, dtype=torch.bool, device=dev)
+                    start[1:] = cs[1:] != cs[:-1]
+                    first = torch.cummax(torch.where(start, ar, torch.zeros_like(ar)), 0).values  # start of each key's run
+                    run = csum - (csum - ws)[first]  # amounts on this counter up to and including each key
+                    vals[order, r] = torch.clamp(table[r * w + cs].to(torch.int64) + run, max=INT32_T_MAX)
+                # the table itself moves through the add kernel (same end state as add_many, saturation included)
+                rows = idx[lo:hi]
+                ea_c = C.c_int64(0)
+                _native.call("pb_cms_add_hashes", self._h, C.c_void_p(rows.data_ptr()), cn, 1,
+                             None if scalar else C.c_void_p(wv.data_ptr()), int(num_els) if scalar else 0, C.byref(ea_c))
+                ea_run = torch.clamp(torch.cumsum(wv, 0) + ea, max=INT64_T_MAX)  # (:283-286; int64 wrap is out of reach here)
+                if self._query_type == "min":
+                    res = vals.min(1).values
+                elif self._query_type == "mean":
+                    res = torch.div(vals.sum(1), d, rounding_mode="floor")
+                else:  # mean-min, :438-453, with elements_added as it stands after this key
+                    srt = torch.sort(vals, 1).values
+                    calc = srt - torch.div(ea_run[:, None] - srt, w - 1, rounding_mode="floor")
+                    calc = torch.sort(calc, 1).values
+                    mid = torch.div(calc[:, d // 2] + calc[:, d // 2 - 1], 2, rounding_mode="floor") if d % 2 == 0 else calc[:, d // 2]
+                    res = torch.where((srt[:, 0] == 0) & (srt[:, -1] == 0), torch.zeros_like(mid), mid)
+                out[lo:hi] = res
+                ea = int(ea_run[-1])
+            self._ctx.synchronize()
+        self._elements_added = ea
+        return out
+
     def check_many(self, keys) -> np.ndarray:
         """CountMinSketch.check (:323-340) for every key -> int64[n] with the current query_type"""
         qt = _QUERY_CODE[self._query_type]
@@ -275,14 +361,17 @@ class CountMinSketch:
             raise IndexError("list index out of range")
         return np.asarray([h if 0 <= h <= _U64_MASK else h % w for h in hs], dtype=np.uint64).reshape(1, d)
 
-    def add_alt(self, hashes, num_els: int = 1) -> int:
-        """:267-288"""
+    def _add_alt_row(self, hashes, num_els: int) -> int:
         row = self._alt_row(hashes)
         ea = C.c_int64(self._elements_added)
         arr, scalar = self._num_els_args(num_els, 1)
         self._add_rows(row, arr, scalar, ea)
         self._elements_added = ea.value
         return int(self._check_rows(row)[0])
+
+    def add_alt(self, hashes, num_els: int = 1) -> int:
+        """:267-288"""
+        return self._add_alt_row(hashes, num_els)
 
     def check_alt(self, hashes) -> int:
         """:332-340"""
@@ -293,7 +382,7 @@ class CountMinSketch:
         return self.add(key, -int(num_els))
 
     def remove_alt(self, hashes, num_els: int = 1) -> int:
-        return self.add_alt(hashes, -int(num_els))
+        return self._add_alt_row(hashes, -int(num_els))
 
     # ------------------------------------------------------------------ merge (:356-399)
     def join(self, second: "CountMinSketch") -> None:
@@ -355,3 +444,202 @@ class CountMeanMinSketch(CountMinSketch):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.query_type = "mean-min"
+
+
+def _batch_key_getter(keys):
+    """index -> the object the reference would use as dictionary key for that element of the batch"""
+    if isinstance(keys, (str, bytes, bytearray, memoryview)):
+        return lambda i: keys
+    if isinstance(keys, np.ndarray):
+        return lambda i: keys[i].tobytes()
+    if type(keys).__module__.startswith("torch"):
+        host = {}
+
+        def get(i):
+            if "a" not in host:
+                host["a"] = keys.cpu().numpy()
+            return host["a"][i].tobytes()
+
+        return get
+    seq = keys if isinstance(keys, (list, tuple)) else list(keys)
+    return lambda i: seq[i]
+
+
+class _TrackingSketch(CountMinSketch):
+    """shared batch plumbing of HeavyHitters and StreamThreshold: the per-key return values of an ordered batch
+    (add_many_returns) and the few of them that can touch the dictionary, brought to the host in order"""
+
+    def _returns_and_getter(self, keys, num_els):
+        if not isinstance(keys, (str, bytes, bytearray, memoryview, np.ndarray, list, tuple)) and not type(keys).__module__.startswith("torch"):
+            keys = list(keys)
+        return self.add_many_returns(keys, num_els), _batch_key_getter(keys), keys
+
+    @staticmethod
+    def _result(res, keys):
+        return res if type(keys).__module__.startswith("torch") and keys.is_cuda else res.cpu().numpy()
+
+
+class HeavyHitters(_TrackingSketch):
+    """countminsketch.py:532-697: a Count-Min sketch that tracks the `num_hitters` most frequent keys in a dictionary.
+    `add_many` applies the reference's one-key-at-a-time bookkeeping (:617-661) to an ordered batch: the value add()
+    would return is computed for every key on the device, and only the keys whose value reaches the smallest tracked
+    count (a superset of those that can change the dictionary) are walked on the host, in order."""
+
+    def __init__(self, num_hitters: int = 100, width=None, depth=None, confidence=None, error_rate=None, filepath=None,
+                 hash_function=None, **kw):
+        super().__init__(width, depth, confidence, error_rate, filepath, hash_function, **kw)
+        self._top_x: dict = {}
+        self._top_x_size = 0
+        self._num_hitters = num_hitters
+        self._smallest = 0
+
+    @classmethod
+    def frombytes(cls, b, num_hitters: int = 100, hash_function=None, **kw) -> "HeavyHitters":
+        """:576-590"""
+        width, depth, _ = _FOOTER.unpack(bytes(b[-_FOOTER.size :]))
+        hh = cls(num_hitters=num_hitters, width=width, depth=depth, hash_function=hash_function, **kw)
+        hh._parse_bytes(bytes(b))
+        return hh
+
+    def __str__(self) -> str:
+        return (f"Heavy Hitters {super().__str__()}\n\tNumber Hitters: {self.number_heavy_hitters}\n"
+                f"\tNumber Recorded: {self._top_x_size}")
+
+    @property
+    def heavy_hitters(self) -> dict:
+        return self._top_x
+
+    @property
+    def number_heavy_hitters(self) -> int:
+        return self._num_hitters
+
+    def _track(self, key, res: int) -> None:
+        """:644-660"""
+        if self._top_x_size < self._num_hitters:
+            tmp = self._top_x.get(key, None)
+            self._top_x[key] = res
+            if tmp is None:
+                self._top_x_size = len(self._top_x)
+        elif key in self._top_x:
+            self._top_x[key] = res
+        elif res > self._smallest:
+            self._top_x[key] = res
+            tmp_key = min(self._top_x, key=self._top_x.get)
+            self._top_x.pop(tmp_key, None)
+            new_min = min(self._top_x, key=self._top_x.get)
+            self._smallest = self._top_x[new_min]
+
+    def add(self, key, num_els: int = 1) -> int:
+        """:617-627"""
+        return self.add_alt(key, self.hashes(key), num_els)
+
+    def add_alt(self, key, hashes, num_els: int = 1) -> int:
+        """:629-661 (note the extra `key` argument, as in the reference)"""
+        res = self._add_alt_row(hashes, num_els)
+        self._track(key, res)
+        return res
+
+    def add_many(self, keys, num_els=1):
+        """HeavyHitters.add for every key of the batch, in order -> the per-key return values"""
+        import torch
+
+        res, key_at, keys = self._returns_and_getter(keys, num_els)
+        n = res.shape[0]
+        pos, step = 0, 4096  # short first slices: the smallest tracked count rises fast and prunes what follows
+        while pos < n:
+            hi = min(pos + step, n)
+            part = res[pos:hi]
+            # a key can change the dictionary only if its value reaches the smallest tracked count as of now: tracked
+            # keys never fall below it, and an untracked key must exceed it (:652); the bound only rises
+            cand = torch.nonzero(part >= self._smallest).flatten()
+            if cand.numel():
+                for i, v in zip(cand.cpu().tolist(), part[cand].cpu().tolist()):
+                    self._track(key_at(pos + i), v)
+            pos, step = hi, min(step * 4, 1 << 22)
+        return self._result(res, keys)
+
+    def remove_alt(self, hashes, num_els: int = 1):
+        """:663-676"""
+        raise NotSupportedError("Unable to remove elements in the HeavyHitters class as it is an un supported action (and does not"
+                                "make sense)!")
+
+    def remove(self, key, num_els: int = 1):
+        return self.remove_alt(self.hashes(key), num_els)
+
+    def clear(self) -> None:
+        """:678-683"""
+        super().clear()
+        self._top_x = {}
+        self._top_x_size = 0
+        self._smallest = 0
+
+    def join(self, second) -> None:
+        """:685-691"""
+        raise NotSupportedError("Joining is not supported for heavy hitters")
+
+
+class StreamThreshold(_TrackingSketch):
+    """countminsketch.py:694-831: a Count-Min sketch with a dictionary of the keys whose estimate reached `threshold`"""
+
+    def __init__(self, threshold: int = 100, width=None, depth=None, confidence=None, error_rate=None, filepath=None,
+                 hash_function=None, **kw):
+        super().__init__(width, depth, confidence, error_rate, filepath, hash_function, **kw)
+        self._threshold = threshold
+        self._meets_threshold: dict = {}
+
+    @classmethod
+    def frombytes(cls, b, threshold: int = 100, hash_function=None, **kw) -> "StreamThreshold":
+        """:735-749"""
+        width, depth, _ = _FOOTER.unpack(bytes(b[-_FOOTER.size :]))
+        st = cls(threshold=threshold, width=width, depth=depth, hash_function=hash_function, **kw)
+        st._parse_bytes(bytes(b))
+        return st
+
+    def __str__(self) -> str:
+        return (f"Stream Threshold {super().__str__()}\n\tThreshold: {self.threshold}\n"
+                f"\tNumber Meeting Threshold: {len(self._meets_threshold)}")
+
+    @property
+    def meets_threshold(self) -> dict:
+        return self._meets_threshold
+
+    @property
+    def threshold(self) -> int:
+        return self._threshold
+
+    def clear(self) -> None:
+        super().clear()
+        self._meets_threshold = {}
+
+    def add(self, key, num_els: int = 1) -> int:
+        return self.add_alt(key, self.hashes(key), num_els)
+
+    def add_alt(self, key, hashes, num_els: int = 1) -> int:
+        """:787-803"""
+        res = self._add_alt_row(hashes, num_els)
+        if res >= self._threshold:
+            self._meets_threshold[key] = res
+        return res
+
+    def add_many(self, keys, num_els=1):
+        """StreamThreshold.add for every key of the batch, in order -> the per-key return values"""
+        import torch
+
+        res, key_at, keys = self._returns_and_getter(keys, num_els)
+        cand = torch.nonzero(res >= self._threshold).flatten()
+        if cand.numel():
+            for i, v in zip(cand.cpu().tolist(), res[cand].cpu().tolist()):
+                self._meets_threshold[key_at(i)] = v  # :801-802
+        return self._result(res, keys)
+
+    def remove(self, key, num_els: int = 1) -> int:
+        return self.remove_alt(key, self.hashes(key), num_els)
+
+    def remove_alt(self, key, hashes, num_els: int = 1) -> int:
+        """:818-831"""
+        res = self._add_alt_row(hashes, -int(num_els))
+        if res < self._threshold:
+            self._meets_threshold.pop(key, None)
+        else:
+            self._meets_threshold[key] = res
+        return res

@@ -33,7 +33,7 @@ from . import _native
 from .bloom import BloomFilter, _is_file
 from .exceptions import RotatingBloomFilterError
 from .hashes import default_fnv_1a, is_default_hash
-from .keys import KeyBatch, pack_keys
+from .keys import device_batch, pack_keys
 
 _FOOTER = struct.Struct("QQQf")  # expandingbloom.py:72
 _U64 = struct.Struct("Q")  # :73
@@ -127,25 +127,6 @@ class ExpandingBloomFilter:
 
         return torch, torch.cuda.ExternalStream(self._ctx.stream, device=f"cuda:{self._ctx.device}")
 
-    def _device_keys(self, kb: KeyBatch) -> KeyBatch:
-        """host-resident batch -> the same batch in device memory (pb_bloom_index_keys takes device keys)"""
-        if kb.on_device:
-            return kb
-        torch, _ = self._torch()
-        dev = f"cuda:{self._ctx.device}"
-        offs = None
-        n_sym = int(kb.c.stride) * kb.n
-        if kb.c.offsets:
-            o = np.frombuffer((C.c_uint64 * (kb.n + 1)).from_address(kb.c.offsets), dtype=np.uint64)
-            n_sym = int(o[-1])
-            offs = torch.from_numpy(o.astype(np.int64)).to(dev)
-        nbytes = n_sym * int(kb.c.sym_width)
-        raw = np.frombuffer((C.c_uint8 * nbytes).from_address(kb.c.data), dtype=np.uint8) if nbytes else np.zeros(0, np.uint8)
-        data = torch.from_numpy(np.concatenate([raw, np.zeros(16, np.uint8)])).to(dev)  # (copy + tail padding)
-        torch.cuda.current_stream(data.device).synchronize()
-        return KeyBatch(data.data_ptr(), offs.data_ptr() if offs is not None else None, kb.n, int(kb.c.stride),
-                        int(kb.c.sym_width), True, (data, offs))
-
     def _rows(self, keys):
         """-> (int64 CUDA tensor [n, k] holding the u64 bit indices, n, keys_were_on_device)"""
         torch, stream = self._torch()
@@ -155,7 +136,7 @@ class ExpandingBloomFilter:
         if self._fused:
             kb = pack_keys(keys)
             was_dev = kb.on_device
-            dkb = self._device_keys(kb)
+            dkb = device_batch(kb, self._ctx.device)
             with torch.cuda.stream(stream):
                 idx = torch.empty((kb.n, k), dtype=torch.int64, device=dev)
                 if kb.n:

@@ -152,3 +152,25 @@ def pack_keys(keys, sync: bool = True) -> KeyBatch:
     if isinstance(keys, Iterable):
         return _pack_sequence(list(keys))
     raise TypeError(f"cannot interpret {type(keys).__name__} as a batch of keys")
+
+
+def device_batch(kb: KeyBatch, device: int) -> KeyBatch:
+    """a host-resident batch copied to device memory (same layout); device batches pass through.  For the entry points
+    that take device keys only (pb_bloom_index_keys)."""
+    if kb.on_device:
+        return kb
+    import torch
+
+    dev = f"cuda:{device}"
+    offs = None
+    n_sym = int(kb.c.stride) * kb.n
+    if kb.c.offsets:
+        o = np.frombuffer((C.c_uint64 * (kb.n + 1)).from_address(kb.c.offsets), dtype=np.uint64)
+        n_sym = int(o[-1])
+        offs = torch.from_numpy(o.astype(np.int64)).to(dev)
+    nbytes = n_sym * int(kb.c.sym_width)
+    raw = np.frombuffer((C.c_uint8 * nbytes).from_address(kb.c.data), dtype=np.uint8) if nbytes else np.zeros(0, np.uint8)
+    data = torch.from_numpy(np.concatenate([raw, np.zeros(16, np.uint8)])).to(dev)  # (copy + tail padding)
+    torch.cuda.current_stream(data.device).synchronize()
+    return KeyBatch(data.data_ptr(), offs.data_ptr() if offs is not None else None, kb.n, int(kb.c.stride), int(kb.c.sym_width),
+                    True, (data, offs))

@@ -279,3 +279,89 @@ def test_counting_cuckoo_expand_full_and_plugin_hash(pb, orc):
     assert p.unique_elements == 700 and p.elements_added == 2000
     assert p.check("w5") == 3 and p.check("w699") == 2 and p.check("zzz") == 0
     assert p.remove("w699") and p.remove("w699") and not p.remove("w699") and p.unique_elements == 699
+
+
+# ---------------------------------------------------------------- HeavyHitters / StreamThreshold (countminsketch.py:532-831)
+def _names(orc, ranks):
+    return [bytes(k).hex() for k in orc.rank_keys(np.asarray(ranks, dtype=np.uint64))]
+
+
+def test_heavy_hitters_vs_reference(pb, orc, golden):
+    import struct
+
+    h = golden["heavy_hitters"]
+    names = _names(orc, h["ranks"])
+    hh = pb.HeavyHitters(num_hitters=h["num_hitters"], width=h["width"], depth=h["depth"])
+    rets = hh.add_many(names)
+    assert md5(struct.pack(f"<{len(rets)}q", *rets.tolist())) == h["returns_md5"]
+    assert hh.heavy_hitters == h["heavy_hitters"] and md5(hh.bins_numpy().tobytes()) == h["bins_md5"]
+    assert hh.elements_added == len(names) and hh.number_heavy_hitters == h["num_hitters"]
+    # the same stream in uneven pieces and single adds
+    two = pb.HeavyHitters(num_hitters=h["num_hitters"], width=h["width"], depth=h["depth"])
+    two.add_many(names[:7]), two.add(names[7]), two.add_many(names[8:12_345]), two.add_many(names[12_345:])
+    assert two.heavy_hitters == h["heavy_hitters"] and md5(two.bins_numpy().tobytes()) == h["bins_md5"]
+    with pytest.raises(pb.NotSupportedError):
+        hh.remove(names[0])
+    with pytest.raises(pb.NotSupportedError):
+        hh.join(two)
+    assert "Heavy Hitters Count-Min Sketch" in str(hh) and f"Number Recorded: {h['num_hitters']}" in str(hh)
+    back = pb.HeavyHitters.frombytes(bytes(hh), num_hitters=5)
+    assert back.check(names[0]) == hh.check(names[0]) and back.heavy_hitters == {}
+    hh.clear()
+    assert hh.heavy_hitters == {} and hh.elements_added == 0
+
+
+def test_stream_threshold_vs_reference(pb, orc, golden):
+    import struct
+
+    t = golden["stream_threshold"]
+    names = _names(orc, golden["heavy_hitters"]["ranks"])
+    st = pb.StreamThreshold(threshold=t["threshold"], width=t["width"], depth=t["depth"])
+    rets = st.add_many(names)
+    assert md5(struct.pack(f"<{len(rets)}q", *rets.tolist())) == t["returns_md5"]
+    assert st.meets_threshold == t["meets_threshold"] and st.threshold == t["threshold"]
+    # remove below the threshold drops the key again (:818-831)
+    top = max(st.meets_threshold, key=st.meets_threshold.get)
+    cnt = st.meets_threshold[top]
+    assert st.remove(top, cnt - t["threshold"] + 1) == t["threshold"] - 1 and top not in st.meets_threshold
+    assert st.add(top, 5) == t["threshold"] + 4 and st.meets_threshold[top] == t["threshold"] + 4
+
+
+@pytest.mark.parametrize("query_type", ["min", "mean", "mean-min"])
+def test_add_many_returns_equals_one_at_a_time(pb, orc, query_type):
+    """every key's own return value inside one batch: heavy collisions (narrow table), per-key amounts, saturation"""
+    rng = np.random.default_rng(11)
+    ranks = np.minimum(rng.zipf(1.2, 200_000), 1 << 40).astype(np.uint64)
+    keys = orc.rank_keys(ranks)
+    amounts = rng.integers(0, 5, keys.shape[0]).astype(np.int64)
+    amounts[1000] = (1 << 31) - 50  # drives the counters of one key to INT32_MAX
+    c = pb.CountMinSketch(width=997, depth=4 if query_type == "mean-min" else 5)
+    c.query_type = query_type
+    o = orc.CMS(997, c.depth, query_type)
+    got = c.add_many_returns(keys[:50_000])
+    want = o.add(orc.pack(keys[:50_000]), 1, want_returns=True)
+    assert (got.cpu().numpy() == want).all() and (c.bins_numpy() == o.bins).all()
+    got = c.add_many_returns(keys[50_000:], amounts[50_000:])
+    want = o.add(orc.pack(keys[50_000:]), amounts[50_000:], want_returns=True)
+    assert (got.cpu().numpy() == want).all() and (c.bins_numpy() == o.bins).all()
+    assert c.elements_added == o.elements_added
+    import torch
+
+    dev = c.add_many_returns(torch.from_numpy(keys[:1000]).cuda(), 2)
+    assert (dev.cpu().numpy() == o.add(orc.pack(keys[:1000]), 2, want_returns=True)).all()
+
+
+def test_heavy_hitters_large_batch_vs_oracle(pb, orc):
+    rng = np.random.default_rng(3)
+    ranks = np.minimum(rng.zipf(1.1, 300_000), 1 << 40).astype(np.uint64)
+    keys = orc.rank_keys(ranks)
+    names = [k.tobytes() for k in keys]
+    hh = pb.HeavyHitters(num_hitters=50, width=1 << 12, depth=5)
+    o = orc.HeavyHitters(50, 1 << 12, 5)
+    got = hh.add_many(keys)  # a numpy batch: dictionary keys are the rows' bytes
+    want = o.add_tracked(names, orc.pack(keys))
+    assert (got == want).all() and hh.heavy_hitters == o.top_x
+    st = pb.StreamThreshold(threshold=500, width=1 << 12, depth=5)
+    os_ = orc.StreamThreshold(500, 1 << 12, 5)
+    st.add_many(keys), os_.add_tracked(names, orc.pack(keys))
+    assert st.meets_threshold == os_.meets and len(os_.meets) > 10

@@ -68,3 +68,18 @@ def test_counting_cuckoo_vs_reference(orc, golden):
     o = orc.CountingCuckoo(e["capacity"], 4, 5)
     o.add(orc.pack([str(i % 400) for i in range(600)]))
     assert md5(o.export()) == e["export_md5"] and len(o.export()) == e["export_len"]
+
+
+def test_heavy_hitters_and_stream_threshold_vs_reference(orc, golden):
+    import struct
+
+    h = golden["heavy_hitters"]
+    names = [bytes(k).hex() for k in orc.rank_keys(np.array(h["ranks"], dtype=np.uint64))]
+    o = orc.HeavyHitters(h["num_hitters"], h["width"], h["depth"])
+    rets = o.add_tracked(names, orc.pack(names))
+    assert md5(struct.pack(f"<{len(rets)}q", *rets.tolist())) == h["returns_md5"]
+    assert o.top_x == h["heavy_hitters"] and md5(o.bins.tobytes()) == h["bins_md5"]
+    t = golden["stream_threshold"]
+    o = orc.StreamThreshold(t["threshold"], t["width"], t["depth"])
+    rets = o.add_tracked(names, orc.pack(names))
+    assert md5(struct.pack(f"<{len(rets)}q", *rets.tolist())) == t["returns_md5"] and o.meets == t["meets_threshold"]
