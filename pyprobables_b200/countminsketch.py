@@ -545,6 +545,8 @@ class HeavyHitters(_TrackingSketch):
 
         res, key_at, keys = self._returns_and_getter(keys, num_els)
         n = res.shape[0]
+        is_tensor = type(keys).__module__.startswith("torch")
+        as_rows = is_tensor or isinstance(keys, np.ndarray)
         pos, step = 0, 4096  # short first slices: the smallest tracked count rises fast and prunes what follows
         while pos < n:
             hi = min(pos + step, n)
@@ -552,11 +554,66 @@ class HeavyHitters(_TrackingSketch):
             # a key can change the dictionary only if its value reaches the smallest tracked count as of now: tracked
             # keys never fall below it, and an untracked key must exceed it (:652); the bound only rises
             cand = torch.nonzero(part >= self._smallest).flatten()
-            if cand.numel():
+            if cand.numel() and as_rows:
+                at = cand + pos
+                rows = keys[at.to(keys.device)].to(res.device) if is_tensor else torch.from_numpy(keys[at.cpu().numpy()]).to(res.device)
+                self._replay_rows(rows, part[cand])
+            elif cand.numel():
                 for i, v in zip(cand.cpu().tolist(), part[cand].cpu().tolist()):
                     self._track(key_at(pos + i), v)
             pos, step = hi, min(step * 4, 1 << 22)
         return self._result(res, keys)
+
+    def _replay_rows(self, rows, vals) -> None:
+        """the bookkeeping of :644-660 for an ordered run of (key row, value) pairs, without a Python step per pair:
+        pairs whose key is tracked only overwrite that key's value (the last one wins), so they are applied in bulk up to
+        the next pair that changes WHICH keys are tracked; only those pairs go through `_track` one by one."""
+        import torch
+
+        length = rows.shape[1]
+        uniq, inv = torch.unique(rows, dim=0, return_inverse=True)
+        uniq_h, gid, val = uniq.cpu().numpy(), inv.cpu().numpy(), vals.cpu().numpy()
+        tracked = np.zeros(uniq_h.shape[0], dtype=bool)  # per distinct key of this run: in the dictionary right now?
+        cur = np.zeros(uniq_h.shape[0], dtype=np.int64)  # its latest value, written back before every structural step
+        dirty = np.zeros(uniq_h.shape[0], dtype=bool)
+        gid_of = {}
+        for k in self._top_x:
+            if isinstance(k, bytes) and len(k) == length:
+                hit = torch.nonzero((uniq == torch.frombuffer(bytearray(k), dtype=torch.uint8).to(uniq.device)).all(1)).flatten()
+                if hit.numel():
+                    gid_of[k] = int(hit[0])
+                    tracked[gid_of[k]] = True
+
+        def flush():
+            for k, g in gid_of.items():
+                if dirty[g]:
+                    self._top_x[k] = int(cur[g])
+                    dirty[g] = False
+
+        block = 8192
+        for lo in range(0, gid.size, block):
+            g, v = gid[lo : lo + block], val[lo : lo + block]
+            while g.size:
+                t = tracked[g]
+                structural = ~t if self._top_x_size < self._num_hitters else ~t & (v > self._smallest)
+                j = int(np.argmax(structural)) if structural.any() else g.size
+                upd = t[:j]
+                cur[g[:j][upd]] = v[:j][upd]  # repeated keys: the last value wins, as one-at-a-time would leave it
+                dirty[g[:j][upd]] = True
+                if j == g.size:
+                    break
+                flush()
+                key = uniq_h[g[j]].tobytes()
+                before = set(self._top_x)
+                self._track(key, int(v[j]))
+                for gone in before - set(self._top_x):
+                    if gone in gid_of:
+                        tracked[gid_of.pop(gone)] = False
+                if key in self._top_x:
+                    gid_of[key] = int(g[j])
+                    tracked[g[j]] = True
+                g, v = g[j + 1 :], v[j + 1 :]
+        flush()
 
     def remove_alt(self, hashes, num_els: int = 1):
         """:663-676"""
@@ -628,8 +685,23 @@ class StreamThreshold(_TrackingSketch):
         res, key_at, keys = self._returns_and_getter(keys, num_els)
         cand = torch.nonzero(res >= self._threshold).flatten()
         if cand.numel():
-            for i, v in zip(cand.cpu().tolist(), res[cand].cpu().tolist()):
-                self._meets_threshold[key_at(i)] = v  # :801-802
+            is_tensor = type(keys).__module__.startswith("torch")
+            if (is_tensor or isinstance(keys, np.ndarray)) and cand.numel() > 256:
+                # array batches: a key's values only rise, so its last write is its largest, and the dictionary keeps the
+                # position of its first write -- one grouped pass on the device instead of a Python step per occurrence
+                rows = keys[cand.to(keys.device)].to(res.device) if is_tensor else torch.from_numpy(keys[cand.cpu().numpy()]).to(res.device)
+                uniq, inv = torch.unique(rows, dim=0, return_inverse=True)
+                g = uniq.shape[0]
+                best = torch.zeros(g, dtype=torch.int64, device=res.device).scatter_reduce_(0, inv, res[cand], "amax", include_self=False)
+                first = torch.full((g,), cand.numel(), dtype=torch.int64, device=res.device).scatter_reduce_(
+                    0, inv, torch.arange(cand.numel(), device=res.device), "amin", include_self=False)
+                order = torch.argsort(first)
+                uniq_h, best_h = uniq[order].cpu().numpy(), best[order].cpu().tolist()
+                for row, v in zip(uniq_h, best_h):
+                    self._meets_threshold[row.tobytes()] = v  # :801-802
+            else:
+                for i, v in zip(cand.cpu().tolist(), res[cand].cpu().tolist()):
+                    self._meets_threshold[key_at(i)] = v  # :801-802
         return self._result(res, keys)
 
     def remove(self, key, num_els: int = 1) -> int:

@@ -15,6 +15,7 @@
 // Bucket overflow (skewed / duplicate keys) falls back to direct REDs, so the result is exact for
 // any input.
 #include <algorithm>
+#include <vector>
 #include <new>
 
 #include "pb_common.cuh"
@@ -233,6 +234,28 @@ __global__ void __launch_bounds__(256)
         bad += (g < b.lo || g >= b.hi) ? 1ull : 0ull;
     }
     if (bad) atomicAdd(stray, bad);
+}
+
+// found[i] = 1 iff one of the filters holds every bit of row i (ExpandingBloomFilter.check_alt, expandingbloom.py:140-147:
+// `any(blm.check_alt(hashes) for blm in self._blooms)`).  One thread per row, first clear bit ends a filter, first
+// full match ends the row: ~2 probes per filter for an absent key instead of k.
+__global__ void __launch_bounds__(256)
+    bloom_rows_in_any_kernel(const uint64_t *__restrict__ idx, uint64_t n, uint32_t k, const uint32_t *const *__restrict__ words,
+                             uint32_t n_filters, uint8_t *__restrict__ found) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t *row = idx + i * k;
+        uint32_t hit = 0;
+        for (uint32_t f = 0; f < n_filters && !hit; ++f) {
+            const uint32_t *w = words[f];
+            uint32_t s = 0;
+            for (; s < k; ++s) {
+                const uint64_t l = row[s];
+                if (!((__ldg(w + (l >> 5)) >> (uint32_t)(l & 31)) & 1u)) break;
+            }
+            hit = s == k;
+        }
+        found[i] = (uint8_t)hit;
+    }
 }
 
 // bloom.py:371-428: res = a | b (op 0) or a & b (op 1), streaming 128-bit words
@@ -1070,6 +1093,31 @@ int pb_bloom_release_scratch(pb_bloom *b) {
     PB_CUDA(cudaFree(b->first_setter));
     b->first_setter = nullptr;
     return PB_OK;
+}
+
+// found_dev[i] = 1 iff one of the n_filters filters (same context, num_bits and k, unsharded) holds every bit of row i
+int pb_bloom_rows_in_any(pb_bloom *const *filters, uint32_t n_filters, const uint64_t *idx_dev, uint64_t n, uint8_t *found_dev) {
+    PB_REQUIRE(filters && n_filters >= 1 && ((idx_dev && found_dev) || n == 0), "bad argument");
+    if (n == 0) return PB_OK;
+    pb_bloom *b0 = filters[0];
+    PB_REQUIRE(b0, "filter handle is NULL");
+    pb_ctx *ctx = b0->ctx;
+    DeviceGuard g(ctx->device);
+    std::vector<const uint32_t *> ptrs(n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) {
+        pb_bloom *b = filters[f];
+        PB_REQUIRE(b && b->ctx == ctx && b->num_bits == b0->num_bits && b->k == b0->k && b->lo_bit == 0 && b->hi_bit == b->num_bits,
+                   "pb_bloom_rows_in_any takes whole filters of one context with equal num_bits and k");
+        ptrs[f] = b->words;
+    }
+    PB_TRY(rows_in_range(b0, idx_dev, n * b0->k));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096 + (size_t)n_filters * 8));
+    const uint32_t **d_ptrs = (const uint32_t **)((uint8_t *)ctx->small.p + 4096);
+    PB_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), (size_t)n_filters * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));  // `ptrs` is pageable host memory of this frame
+    launch_begin(ctx);
+    bloom_rows_in_any_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, b0->k, d_ptrs, n_filters, found_dev);
+    return check_launch(ctx, "bloom_rows_in_any");
 }
 
 }  // extern "C"

@@ -517,18 +517,24 @@ struct FpCounts {
     uint64_t mask;  // cap - 1; index cap = fingerprint 0
 };
 
-__device__ __forceinline__ uint64_t counts_claim(const FpCounts &m, uint32_t fp, unsigned long long *used) {
+// `claimed` counts the entries this thread took for a fingerprint the map had not seen (callers add the per-thread
+// totals up once per warp: one global atomic per new fingerprint would serialise a batch of new keys on one address)
+__device__ __forceinline__ uint64_t counts_claim(const FpCounts &m, uint32_t fp, unsigned long long &claimed) {
     if (fp == 0u) return m.mask + 1;
     uint64_t s = sm64((uint64_t)fp) & m.mask;
     for (;;) {
         const uint32_t old = atomicCAS(m.keys + s, 0u, fp);
         if (old == 0u) {
-            atomicAdd(used, 1ull);
+            ++claimed;
             return s;
         }
         if (old == fp) return s;
         s = (s + 1) & m.mask;
     }
+}
+__device__ __forceinline__ void counts_flush_claimed(unsigned long long claimed, unsigned long long *used) {
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(used, claimed);
 }
 // index of fp's entry, or ~0 when the map never saw it
 __device__ __forceinline__ uint64_t counts_find(const FpCounts &m, uint32_t fp) {
@@ -545,10 +551,12 @@ __device__ __forceinline__ uint64_t counts_find(const FpCounts &m, uint32_t fp) 
 // (fps may hold 32-bit hashes still to be cut to fp_bits, as in the set kernels above: the cut is idempotent)
 __global__ void __launch_bounds__(256) counts_add_kernel(const uint32_t *__restrict__ fps, const uint32_t *__restrict__ amounts, uint64_t n,
                                                          uint32_t fp_bits, FpCounts m, unsigned long long *used) {
+    unsigned long long claimed = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], fp_bits);
-        atomicAdd(m.vals + counts_claim(m, fp, used), amounts ? amounts[i] : 1u);  // :165-171 / :230-241
+        atomicAdd(m.vals + counts_claim(m, fp, claimed), amounts ? amounts[i] : 1u);  // :165-171 / :230-241
     }
+    counts_flush_claimed(claimed, used);
 }
 __global__ void __launch_bounds__(256) counts_get_kernel(const uint32_t *__restrict__ fps, uint64_t n, uint32_t fp_bits, FpCounts m,
                                                          uint32_t *__restrict__ out) {
@@ -559,8 +567,10 @@ __global__ void __launch_bounds__(256) counts_get_kernel(const uint32_t *__restr
 }
 __global__ void __launch_bounds__(256) counts_set_kernel(const uint32_t *__restrict__ fps, const uint32_t *__restrict__ vals, uint64_t n,
                                                          FpCounts m, unsigned long long *used) {
+    unsigned long long claimed = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        m.vals[counts_claim(m, fps[i], used)] = vals ? vals[i] : 0u;
+        m.vals[counts_claim(m, fps[i], claimed)] = vals ? vals[i] : 0u;
+    counts_flush_claimed(claimed, used);
 }
 // remove, pass 1: every occurrence of a stored fingerprint draws a ticket; tickets below the count are the removals
 // that succeed (:199-208: a key removed more often than it was added runs dry).  The counts do not move in this pass.
@@ -580,6 +590,7 @@ template <int BS>
 __global__ void __launch_bounds__(256) counts_remove_settle(const uint32_t *__restrict__ fps, const uint64_t *__restrict__ i2_in, uint64_t n,
                                                             CuckooDev c, FpCounts m, const uint32_t *__restrict__ ticket_of,
                                                             unsigned long long *totals /* [0] removed, [1] bins removed */) {
+    unsigned long long removed = 0, bins = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         if (ticket_of[i] != 0u) continue;
         const uint32_t fp = cuckoo_fingerprint((uint64_t)fps[i], c.fp_bits);
@@ -588,7 +599,7 @@ __global__ void __launch_bounds__(256) counts_remove_settle(const uint32_t *__re
         const uint32_t dec = drawn < have ? drawn : have;
         m.vals[s] = have - dec;
         m.tickets[s] = 0u;
-        atomicAdd(totals, (unsigned long long)dec);
+        removed += dec;
         if (have == dec) {
             bool hit;
             if (fp == 0u) {
@@ -599,18 +610,22 @@ __global__ void __launch_bounds__(256) counts_remove_settle(const uint32_t *__re
                 if (i2_in) i2 = i2_in[i];
                 hit = bucket_take<BS>(c, i1, fp) || bucket_take<BS>(c, i2, fp);
             }
-            if (hit) atomicAdd(totals + 1, 1ull);
+            bins += hit;
         }
     }
+    counts_flush_claimed(removed, totals);
+    counts_flush_claimed(bins, totals + 1);
 }
 __global__ void __launch_bounds__(256) counts_rehash_kernel(FpCounts from, FpCounts to, unsigned long long *used) {
     const uint64_t n = from.mask + 2;  // incl. the entry of fingerprint 0
+    unsigned long long claimed = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t v = from.vals[i];
         if (v == 0u) continue;
         if (i == from.mask + 1) to.vals[to.mask + 1] = v;
-        else to.vals[counts_claim(to, from.keys[i], used)] = v;
+        else to.vals[counts_claim(to, from.keys[i], claimed)] = v;
     }
+    counts_flush_claimed(claimed, used);
 }
 
 // ---------------------------------------------------------------- host side

@@ -156,16 +156,11 @@ class ExpandingBloomFilter:
     def _found(self, blooms, idx):
         """uint8 CUDA tensor [n]: 1 where a filter of `blooms` holds every bit of the row (:140-147)"""
         torch, _ = self._torch()
-        n, k = idx.shape
+        n = idx.shape[0]
         found = torch.zeros(n, dtype=torch.uint8, device=idx.device)
-        if n == 0:
-            return found
-        bits = torch.empty(n * k, dtype=torch.uint8, device=idx.device)
-        one = torch.empty(n, dtype=torch.uint8, device=idx.device)
-        for blm in blooms:
-            _native.call("pb_bloom_test_bit_indices", blm._h, C.c_void_p(idx.data_ptr()), n * k, C.c_void_p(bits.data_ptr()))
-            _native.call("pb_bloom_and_rows", self._ctx.handle, C.c_void_p(bits.data_ptr()), n, k, C.c_void_p(one.data_ptr()))
-            found |= one
+        if n and blooms:
+            handles = (C.c_void_p * len(blooms))(*[b._h.value for b in blooms])
+            _native.call("pb_bloom_rows_in_any", handles, len(blooms), C.c_void_p(idx.data_ptr()), n, C.c_void_p(found.data_ptr()))
         return found
 
     # ------------------------------------------------------------------ check (:130-147)
