@@ -130,6 +130,38 @@ __device__ __forceinline__ bool bucket_place_from(const CuckooDev &c, uint64_t b
     return false;
 }
 
+// Placement that doubles as the in-batch dedupe of the first kernel.  While that kernel runs, slots only ever go from
+// empty to occupied, and every thread walks the empty slots of idx_1, then idx_2, in the same order with a CAS each:
+// two threads that carry the same fingerprint meet on the first slot either of them wins -- the loser's CAS hands it
+// its own fingerprint back.  kPlaced / kTwin (the same fingerprint got there first: nothing to do) / kNoRoom.
+enum : int { kNoRoom = 0, kPlaced = 1, kTwin = 2 };
+__device__ __forceinline__ int slot_try(uint32_t *s, uint32_t fp) {
+    const uint32_t old = atomicCAS(s, 0u, fp);
+    return old == 0u ? kPlaced : (old == fp ? kTwin : kNoRoom);
+}
+__device__ __forceinline__ int bucket_place_dedupe(const CuckooDev &c, uint64_t b, uint32_t fp, const uint4 &v) {
+    uint32_t *s = c.slots + b * 4;
+    int r;
+    if (v.x == 0 && (r = slot_try(s + 0, fp)) != kNoRoom) return r;
+    if (v.y == 0 && (r = slot_try(s + 1, fp)) != kNoRoom) return r;
+    if (v.z == 0 && (r = slot_try(s + 2, fp)) != kNoRoom) return r;
+    if (v.w == 0 && (r = slot_try(s + 3, fp)) != kNoRoom) return r;
+    return kNoRoom;
+}
+template <int BS>
+__device__ __forceinline__ int bucket_place_dedupe_any(const CuckooDev &c, uint64_t b, uint32_t fp) {
+    uint32_t *s = c.slots + b * c.bucket_size;
+    for (uint32_t j = 0; j < c.bucket_size; ++j) {
+        const uint32_t cur = __ldcg(s + j);
+        if (cur == fp) return kTwin;
+        if (cur == 0u) {
+            const int r = slot_try(s + j, fp);
+            if (r != kNoRoom) return r;
+        }
+    }
+    return kNoRoom;
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x) { return sm64(x); }
 
 // cuckoo.py:361-392 for one fingerprint that is known to be absent.  Returns true when everything found
@@ -200,30 +232,39 @@ __device__ __forceinline__ void claim_filter(const CuckooDev &c, uint32_t fp, bo
         if (fp == 0u) {
             // the zero fingerprint lives in the flag word; the flag itself is the claim
             if (atomicExch(c.zero_flag, 1u) == 0u) placed = 1;
-        } else if (claim_fp(c, fp)) {  // this thread owns fp for the batch
+        } else {
             uint64_t i1, i2;
             cuckoo_buckets(c, fp, i1, i2);
+            int r;
+            bool present;
             if (BS == 4) {
                 // both buckets in flight together; the snapshots serve the presence test (:300-302) AND the first
                 // placement attempt (:363-368): the CAS hits the sector the load has just brought into L2, and the
-                // second kernel only ever sees fingerprints whose two buckets were full (r2: it used to re-read both
-                // buckets of every new fingerprint from DRAM)
+                // second kernel only ever sees fingerprints whose two buckets were full
                 const uint4 v1 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i1);
                 const uint4 v2 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i2);
                 const bool in1 = v1.x == fp || v1.y == fp || v1.z == fp || v1.w == fp;
                 const bool in2 = v2.x == fp || v2.y == fp || v2.z == fp || v2.w == fp;
-                if (!(in1 | in2)) {
-                    if (bucket_place_from(c, i1, fp, v1) || bucket_place_from(c, i2, fp, v2)) placed = 1;
-                    else is_new = true;
+                present = in1 | in2;
+                r = kNoRoom;
+                if (!present) {
+                    r = bucket_place_dedupe(c, i1, fp, v1);
+                    if (r == kNoRoom) r = bucket_place_dedupe(c, i2, fp, v2);
                 }
             } else {
-                const bool in1 = bucket_has<BS>(c, i1, fp);
-                const bool in2 = bucket_has<BS>(c, i2, fp);
-                if (!(in1 | in2)) {
-                    if (bucket_place<BS>(c, i1, fp) || bucket_place<BS>(c, i2, fp)) placed = 1;
-                    else is_new = true;
+                present = bucket_has<BS>(c, i1, fp) || bucket_has<BS>(c, i2, fp);
+                r = kNoRoom;
+                if (!present) {
+                    r = bucket_place_dedupe_any<BS>(c, i1, fp);
+                    if (r == kNoRoom) r = bucket_place_dedupe_any<BS>(c, i2, fp);
                 }
             }
+            // Repeats of one fingerprint inside the batch sort themselves out on the slots (see bucket_place_dedupe); only
+            // the fingerprints that found both buckets full -- none at low load -- need the claim set, so that exactly
+            // one copy of each goes on to the eviction walk.  (r2: one claim atomic per KEY in a 512 MiB bitmap was a
+            // quarter of this kernel's random DRAM accesses.)
+            if (r == kPlaced) placed = 1;
+            else if (!present && r == kNoRoom) is_new = claim_fp(c, fp);
         }
     }
     // warp-aggregated counters and append to the list of fingerprints that need the eviction walk
