@@ -82,7 +82,7 @@ struct CuckooCounters {  // device-resident, zeroed per call
     unsigned long long n_new;     // fingerprints handed to the insert kernel
     unsigned long long n_placed;  // fingerprints newly stored
     unsigned long long n_failed;  // homeless fingerprints
-    unsigned long long pad;
+    unsigned long long cursor;    // next list entry the insert kernel hands out
 };
 
 __device__ __forceinline__ void cuckoo_buckets(const CuckooDev &c, uint32_t fp, uint64_t &i1, uint64_t &i2) {
@@ -164,6 +164,44 @@ __device__ __forceinline__ int bucket_place_dedupe_any(const CuckooDev &c, uint6
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) { return sm64(x); }
 
+// One eviction step of cuckoo.py:375-388 for the fingerprint in hand: pick the victim in bucket idx, swap, try the
+// victim's other bucket.  true = everything has a home now.
+template <int BS>
+__device__ __forceinline__ bool cuckoo_walk_step(const CuckooDev &c, uint32_t &fp, uint64_t &idx, uint64_t &rng) {
+    rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+    uint32_t slot = (uint32_t)(((rng >> 33) * (uint64_t)c.bucket_size) >> 31);  // :377 (uniform in [0,bs))
+    if (BS == 4) {
+        // Informed choice of the victim (the reference draws it at random, :377; any choice leaves the same set of
+        // stored fingerprints): look at the other bucket of all four residents at once -- four loads in flight, one
+        // round trip -- and evict one that has room there, so that the walk ends with this step.
+        const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + idx);
+        const uint32_t res[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint4 alt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint64_t a, b;
+            cuckoo_buckets(c, res[j], a, b);
+            alt[j] = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + ((idx == a) ? b : a));
+        }
+        const uint32_t start = slot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = (start + j) & 3u;
+            if (res[q] == 0u || (alt[q].x == 0u || alt[q].y == 0u || alt[q].z == 0u || alt[q].w == 0u)) {
+                slot = q;
+                break;
+            }
+        }
+    }
+    const uint32_t victim = atomicExch(c.slots + idx * c.bucket_size + slot, fp);  // :379-380
+    if (victim == 0u) return true;  // the slot was (still) empty: nobody was evicted
+    fp = victim;
+    uint64_t a, b;
+    cuckoo_buckets(c, fp, a, b);  // :383
+    idx = (idx == a) ? b : a;     // :385
+    return bucket_place<BS>(c, idx, fp);  // :387-388
+}
+
 // cuckoo.py:361-392 for one fingerprint that is known to be absent.  Returns true when everything found
 // a home; false with `fp` = the homeless fingerprint.
 template <int BS>
@@ -183,42 +221,8 @@ __device__ __forceinline__ bool cuckoo_insert_one(const CuckooDev &c, uint32_t &
     }
     rng = mix64(rng ^ fp);
     uint64_t idx = (rng & 1ull) ? i2 : i1;  // :373
-    for (uint32_t s = 0; s < c.max_swaps; ++s) {
-        rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
-        uint32_t slot = (uint32_t)(((rng >> 33) * (uint64_t)c.bucket_size) >> 31);  // :377 (uniform in [0,bs))
-        if (BS == 4) {
-            // Informed choice of the victim (the reference draws it at random, :377; any choice leaves the same set of
-            // stored fingerprints): look at the other bucket of all four residents at once -- four loads in flight,
-            // one round trip -- and evict one that has room there, so that the walk ends at the next step instead of
-            // wandering.  At 85-95 % load this is what the insert time is made of (r2 ncu: 4.3 G instructions for the
-            // batch that takes the table from 50 % to 93 %).
-            const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + idx);
-            const uint32_t res[4] = {cur.x, cur.y, cur.z, cur.w};
-            uint4 alt[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint64_t a, b;
-                cuckoo_buckets(c, res[j], a, b);
-                alt[j] = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + ((idx == a) ? b : a));
-            }
-            const uint32_t start = slot;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t q = (start + j) & 3u;
-                if (res[q] == 0u || (alt[q].x == 0u || alt[q].y == 0u || alt[q].z == 0u || alt[q].w == 0u)) {
-                    slot = q;
-                    break;
-                }
-            }
-        }
-        const uint32_t victim = atomicExch(c.slots + idx * c.bucket_size + slot, fp);     // :379-380
-        if (victim == 0u) return true;  // the slot was (still) empty: nobody was evicted
-        fp = victim;
-        uint64_t a, b;
-        cuckoo_buckets(c, fp, a, b);  // :383
-        idx = (idx == a) ? b : a;     // :385
-        if (bucket_place<BS>(c, idx, fp)) return true;  // :387-388
-    }
+    for (uint32_t s = 0; s < c.max_swaps; ++s)
+        if (cuckoo_walk_step<BS>(c, fp, idx, rng)) return true;
     return false;  // :392
 }
 
@@ -344,21 +348,88 @@ __global__ void __launch_bounds__(256) cuckoo_fp_fixed16(const uint4 *__restrict
 }
 
 // ---- kernel 2: insert distinct, absent fingerprints ---------------------------------------------------
+// A work queue instead of one list entry per thread: walks differ in length (most end after one step, some take tens),
+// and with a fixed assignment a warp runs for as long as its longest walk with most lanes idle (r2 ncu at 93 % load:
+// 4.3 G warp instructions for 37 M walks, issue slots 47 % busy -- this kernel was instruction bound).  Every lane that
+// finishes takes the next entry, so a warp's instruction count follows the AVERAGE walk.
 // skip_zero: the list is an old slot array (expand, :467-481) whose zeros are empty slots.
 template <int BS>
 __global__ void __launch_bounds__(256) cuckoo_insert_kernel(const uint32_t *__restrict__ list, const unsigned long long *n_ptr,
                                                             uint64_t n_fixed, int skip_zero, CuckooDev c, uint64_t rng_seed,
                                                             uint32_t *__restrict__ failed, uint64_t failed_cap, CuckooCounters *cnt) {
     const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
+    const uint32_t warp = __activemask();  // (the in-order variant launches a single thread)
+    const uint32_t lane = threadIdx.x & 31u;
     unsigned long long placed = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t fp = list[i];
-        if (skip_zero && fp == 0u) continue;
-        if (cuckoo_insert_one<BS>(c, fp, rng_seed + i * 0x9E3779B97F4A7C15ULL)) {
-            ++placed;
-        } else {
-            const unsigned long long pos = atomicAdd(&cnt->n_failed, 1ull);
-            if (pos < failed_cap) failed[pos] = fp;
+    uint32_t fp = 0, steps = 0;
+    uint64_t idx = 0, rng = 0;
+    bool busy = false, fresh = false, drained = false;
+    uint64_t q_next = 0, q_end = 0;  // this warp's current block of list entries (warp-uniform)
+    constexpr uint64_t kBlock = 128;  // entries per trip to the global cursor
+    for (;;) {
+        const uint32_t idle = __ballot_sync(warp, !busy);
+        if (idle && !drained) {
+            if (q_next == q_end) {
+                unsigned long long base = 0;
+                const int leader = __ffs(warp) - 1;
+                if ((int)lane == leader) base = atomicAdd(&cnt->cursor, (unsigned long long)kBlock);
+                base = __shfl_sync(warp, base, leader);
+                q_next = base < n ? base : n;
+                q_end = base + kBlock < n ? base + kBlock : n;
+            }
+            const uint64_t avail = q_end - q_next;
+            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            if (!busy && rank < avail) {
+                const uint64_t i = q_next + rank;
+                fp = list[i];
+                if (!(skip_zero && fp == 0u)) {
+                    busy = fresh = true;
+                    rng = rng_seed + i * 0x9E3779B97F4A7C15ULL;
+                }
+            }
+            const uint64_t want = (uint64_t)__popc(idle);
+            q_next += want < avail ? want : avail;
+            drained = q_next >= n;
+        }
+        if (!__any_sync(warp, busy)) {
+            if (drained) break;
+            continue;  // (only zeros of an old slot array were drawn: draw again)
+        }
+        if (busy) {
+            bool done = false;
+            if (fresh) {
+                fresh = false;
+                uint64_t i1, i2;
+                cuckoo_buckets(c, fp, i1, i2);
+                // entries of an add batch found both buckets full in the first kernel, and slots never empty again
+                // while a batch is being added: only an old slot array (expand) has to try the plain placement here
+                if (skip_zero) {
+                    if (BS == 4) {
+                        const uint4 v1 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i1);
+                        const uint4 v2 = __ldcg(reinterpret_cast<const uint4 *>(c.slots) + i2);
+                        done = bucket_place_from(c, i1, fp, v1) || bucket_place_from(c, i2, fp, v2);  // :363-368
+                    } else {
+                        done = bucket_place<BS>(c, i1, fp) || bucket_place<BS>(c, i2, fp);
+                    }
+                }
+                rng = mix64(rng ^ fp);
+                idx = (rng & 1ull) ? i2 : i1;  // :373
+                steps = 0;
+            }
+            if (done) {
+                // placed without a walk
+            } else if (steps < c.max_swaps) {
+                ++steps;
+                done = cuckoo_walk_step<BS>(c, fp, idx, rng);
+            } else {  // :392 -- out of swaps: the fingerprint in hand is homeless
+                const unsigned long long pos = atomicAdd(&cnt->n_failed, 1ull);
+                if (pos < failed_cap) failed[pos] = fp;
+                busy = false;
+            }
+            if (done) {
+                ++placed;
+                busy = false;
+            }
         }
     }
     if (placed) atomicAdd(&cnt->n_placed, placed);  // one per thread: noise next to the table traffic
