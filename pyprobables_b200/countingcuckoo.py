@@ -54,6 +54,21 @@ class CountingCuckooFilter(CuckooFilter):
         super()._create()
         _native.call("pb_cuckoo_counts_enable", self._h)
 
+    def _set_fingerprint_bits(self, bits: int) -> None:
+        """as CuckooFilter; the counts of a live filter move over to the re-created handle"""
+        live = (getattr(self, "_h", None) is not None and getattr(self, "_inserted", 0) > 0
+                and getattr(self, "_fingerprint_bits", None) != bits)
+        if live:
+            slots, has_zero = self.slots_numpy()
+            stored = slots[slots != 0]
+            if has_zero:
+                stored = np.concatenate([stored, np.zeros(1, np.uint32)])
+            stored = np.ascontiguousarray(stored, dtype=np.uint32)
+            counts = self._counts_of(stored)
+        super()._set_fingerprint_bits(bits)
+        if live and stored.size:
+            _native.call("pb_cuckoo_counts_set", self._h, C.c_void_p(stored.ctypes.data), C.c_void_p(counts.ctypes.data), stored.size)
+
     @property
     def elements_added(self) -> int:
         return self._total

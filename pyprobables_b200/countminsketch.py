@@ -704,6 +704,10 @@ class StreamThreshold(_TrackingSketch):
                     self._meets_threshold[key_at(i)] = v  # :801-802
         return self._result(res, keys)
 
+    def join(self, second) -> None:
+        """:837-843"""
+        raise NotSupportedError("Joining is not supported for stream threshold")
+
     def remove(self, key, num_els: int = 1) -> int:
         return self.remove_alt(key, self.hashes(key), num_els)
 

@@ -365,3 +365,234 @@ def test_heavy_hitters_large_batch_vs_oracle(pb, orc):
     os_ = orc.StreamThreshold(500, 1 << 12, 5)
     st.add_many(keys), os_.add_tracked(names, orc.pack(keys))
     assert st.meets_threshold == os_.meets and len(os_.meets) > 10
+
+
+# ---------------------------------------------------------------- the reference's own test literals for the wrappers
+class _serial:
+    """key-order insertion (one device thread): reproduces the reference's slot order, which its export md5s pin"""
+
+    def __init__(self, pb):
+        self.ctx = pb.default_context()
+
+    def __enter__(self):
+        self.ctx.set_option("cuckoo_serial", 1)
+
+    def __exit__(self, *a):
+        self.ctx.set_option("cuckoo_serial", 0)
+
+
+def test_counting_cuckoo_reference_test_file(pb, tmp_path):
+    # tests/countingcuckoo_test.py:24-46 constructor properties
+    cko = pb.CountingCuckooFilter()
+    assert (cko.capacity, cko.bucket_size, cko.max_swaps, cko.expansion_rate, cko.auto_expand) == (10000, 4, 500, 2, True)
+    cko = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=5, expansion_rate=4, auto_expand=False)
+    assert (cko.capacity, cko.bucket_size, cko.max_swaps, cko.expansion_rate, cko.auto_expand) == (100, 2, 5, 4, False)
+    # :100-128 lots / full
+    cko = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=100)
+    cko.add_many([str(i) for i in range(125)])
+    assert cko.elements_added == 125
+    with pytest.raises(pb.CuckooFilterFullError) as ex:
+        full = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=100, auto_expand=False)
+        for i in range(175):
+            full.add(str(i))
+    assert str(ex.value) == "The CountingCuckooFilter is currently full"
+    # :177-197 load factor
+    cko = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=10)
+    assert cko.load_factor() == 0.0
+    cko.add_many([str(i) for i in range(50)])
+    assert cko.load_factor() == 0.25
+    cko.add_many([str(i + 50) for i in range(50)])
+    assert cko.load_factor() == (0.25 if cko.capacity == 200 else 0.50)
+    cko.add_many([str(i) for i in range(100)])
+    assert cko.load_factor() == (0.25 if cko.capacity == 200 else 0.50) and cko.elements_added == 200
+    # :199-253 export / bytes / frombytes / load
+    with _serial(pb):
+        cko = pb.CountingCuckooFilter(capacity=1000, bucket_size=2, auto_expand=False)
+        for i in range(100):
+            cko.add(str(i))
+    assert md5(bytes(cko)) == "6a98c2df1ec9fbb4f75f8e6392696b9b"
+    path = tmp_path / "c.cck"
+    cko.export(path)
+    assert md5(path.read_bytes()) == "6a98c2df1ec9fbb4f75f8e6392696b9b"
+    cko2 = pb.CountingCuckooFilter.frombytes(bytes(cko))
+    assert bytes(cko2) == bytes(cko) and all(cko2.check(str(i)) for i in range(100)) and not cko2.check("999")
+    ckf = pb.CountingCuckooFilter(filepath=path)
+    assert (ckf.check_many([str(i) for i in range(100)]) == 1).all()
+    assert (ckf.capacity, ckf.bucket_size, ckf.max_swaps, ckf.load_factor()) == (1000, 2, 500, 0.05)
+    # :255-273 expand
+    cko = pb.CountingCuckooFilter()
+    cko.add_many([str(i) for i in range(200)])
+    cko.expand()
+    assert (cko.check_many([str(i) for i in range(200)]) > 0).all() and cko.capacity == 20000
+    cko = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=100)
+    for i in range(375):
+        cko.add(str(i))
+    assert cko.capacity == 400 and cko.elements_added == 375 and (cko.check_many([str(i) for i in range(375)]) > 0).all()
+    # :275-300 bin repr / str
+    cko = pb.CountingCuckooFilter(capacity=1, bucket_size=2, max_swaps=100)
+    cko.add("this is a test")
+    assert str(cko.buckets[0]) == "[(fingerprint:4280557824 count:1)]"
+    cko = pb.CountingCuckooFilter(capacity=100, bucket_size=2, max_swaps=100)
+    cko.add_many([str(i) for i in range(75)])
+    assert str(cko) == ("CountingCuckooFilter:\n\tCapacity: 100\n\tTotal Bins: 200\n\tLoad Factor: 37.5%\n\tInserted Elements: 75\n"
+                        "\tMax Swaps: 100\n\tExpansion Rate: 2\n\tAuto Expand: True")
+
+
+def test_counting_cuckoo_error_rate_reference_test_file(pb, tmp_path):
+    # tests/countingcuckoo_test.py:302-420
+    cko = pb.CountingCuckooFilter.init_error_rate(0.00001)
+    assert (cko.capacity, cko.bucket_size, cko.max_swaps, cko.expansion_rate, cko.auto_expand) == (10000, 4, 500, 2, True)
+    assert (cko.fingerprint_size, cko.fingerprint_size_bits, cko.error_rate) == (3, 20, 0.00001)
+    for w in ("this is a test", "this is another test", "this is yet another test"):
+        cko.add(w)
+    assert cko.elements_added == 3 and cko.check("this is a test") and "this is yet another test" in cko
+    assert not cko.check("this is not another test") and "this is not a test" not in cko
+    with _serial(pb):
+        cko = pb.CountingCuckooFilter.init_error_rate(0.00001)
+        for i in range(1000):
+            cko.add(str(i))
+        assert md5(bytes(cko)) == "f68767bd97b21426f5d2315fb38961ad"
+        cko = pb.CountingCuckooFilter.init_error_rate(0.00001)
+        for i in range(1000):
+            cko.add(str(i))
+            if i % 2 == 1:
+                cko.add(str(i))
+    path = tmp_path / "c.cko"
+    cko.export(path)
+    assert md5(path.read_bytes()) == "88bc3a08bfc967f9ba60e9d57c21207f"
+    ckf = pb.CountingCuckooFilter.load_error_rate(error_rate=0.00001, filepath=path)
+    assert ckf.check_many([str(i) for i in range(1000)]).tolist() == [(i % 2) + 1 for i in range(1000)]
+    assert (ckf.capacity, ckf.bucket_size, ckf.max_swaps, ckf.expansion_rate, ckf.auto_expand) == (10000, 4, 500, 2, True)
+    assert (ckf.fingerprint_size_bits, ckf.fingerprint_size, ckf.error_rate, ckf.load_factor()) == (20, 3, 0.00001, 0.025)
+    cko = pb.CountingCuckooFilter.init_error_rate(0.00001, capacity=3000)
+    cko.add_many([str(i) for i in range(1000)])
+    cko2 = pb.CountingCuckooFilter.frombytes(bytes(cko), error_rate=0.00001)
+    assert bytes(cko2) == bytes(cko) and (cko2.check_many([str(i) for i in range(1000)]) > 0).all()
+    assert not cko2.check("9999") and cko2.capacity == 3000
+
+
+def test_heavy_hitters_reference_test_file(pb, tmp_path):
+    # tests/countminsketch_test.py:567-735
+    for kw in ({"width": 1000, "depth": 5}, {"confidence": 0.96875, "error_rate": 0.002}):
+        hh1 = pb.HeavyHitters(num_hitters=1000, **kw)
+        assert (hh1.width, hh1.depth, hh1.confidence, hh1.error_rate, hh1.elements_added) == (1000, 5, 0.96875, 0.002, 0)
+        assert hh1.heavy_hitters == {} and hh1.number_heavy_hitters == 1000
+    hh1 = pb.HeavyHitters(num_hitters=2, width=1000, depth=5)
+    assert [hh1.add("this is a test") for _ in range(3)] == [1, 2, 3]
+    assert hh1.add("this is also a test") == 1 and hh1.add("this is not a test") == 1 and hh1.add("this is not a test") == 2
+    assert hh1.heavy_hitters == {"this is a test": 3, "this is not a test": 2}
+    assert [hh1.add("this is also a test") for _ in range(3)] == [2, 3, 4]
+    assert hh1.heavy_hitters == {"this is a test": 3, "this is also a test": 4}
+    hh1 = pb.HeavyHitters(num_hitters=2, width=1000, depth=5)
+    assert hh1.add("this is a test", 3) == 3 and hh1.add("this is also a test") == 1 and hh1.add("this is not a test", 2) == 2
+    assert hh1.heavy_hitters == {"this is a test": 3, "this is not a test": 2}
+    assert hh1.add("this is also a test", 3) == 4
+    assert hh1.heavy_hitters == {"this is a test": 3, "this is also a test": 4}
+    assert [hh1.add("this is not a test", 2) for _ in range(4)] == [4, 6, 8, 10]
+    assert hh1.heavy_hitters == {"this is not a test": 10, "this is also a test": 4}
+    # the same sequence as ONE ordered batch with per-key amounts
+    hb = pb.HeavyHitters(num_hitters=2, width=1000, depth=5)
+    seq = ["this is a test", "this is also a test", "this is not a test", "this is also a test"] + ["this is not a test"] * 4
+    assert hb.add_many(seq, np.array([3, 1, 2, 3, 2, 2, 2, 2])).tolist() == [3, 1, 2, 4, 4, 6, 8, 10]
+    assert hb.heavy_hitters == {"this is not a test": 10, "this is also a test": 4}
+    with pytest.raises(pb.NotSupportedError) as ex:
+        hh1.remove("this is a test")
+    assert str(ex.value) == ("Unable to remove elements in the HeavyHitters class as it is an un supported action (and does not"
+                             "make sense)!")
+    hh1 = pb.HeavyHitters(num_hitters=1000, width=1000, depth=5)
+    assert hh1.add("this is a test", 100) == 100 and hh1.elements_added == 100 and hh1.heavy_hitters == {"this is a test": 100}
+    assert md5(bytes(hh1)) == "fb1c39dd1a73f1ef0d7fc79f60fc028e"
+    path = tmp_path / "h.cms"
+    hh1.export(path)
+    assert md5(path.read_bytes()) == "fb1c39dd1a73f1ef0d7fc79f60fc028e"
+    hh2 = pb.HeavyHitters(num_hitters=1000, filepath=path)
+    assert (hh2.width, hh2.depth, hh2.elements_added, hh2.check("this is a test"), hh2.heavy_hitters) == (1000, 5, 100, 100, {})
+    assert hh2.add("this is a test", 1) == 101 and hh2.heavy_hitters == {"this is a test": 101}
+    hh3 = pb.HeavyHitters.frombytes(bytes(hh1), num_hitters=500)
+    assert (hh3.width, hh3.depth, hh3.number_heavy_hitters, hh3.elements_added) == (1000, 5, 500, 100)
+    assert bytes(hh3) == bytes(hh1) and hh3.check("this is a test") == 100
+    hs = pb.HeavyHitters(num_hitters=2, width=1000, depth=5)
+    hs.add("this is a test", 100)
+    assert str(hs) == ("Heavy Hitters Count-Min Sketch:\n\tWidth: 1000\n\tDepth: 5\n\tConfidence: 0.96875\n\tError Rate: 0.002\n"
+                       "\tElements Added: 100\n\tNumber Hitters: 2\n\tNumber Recorded: 1")
+    hh1.clear()
+    assert hh1.elements_added == 0 and hh1.heavy_hitters == {}
+
+
+def test_stream_threshold_reference_test_file(pb, tmp_path):
+    # tests/countminsketch_test.py:759-944
+    for kw in ({"width": 1000, "depth": 5}, {"confidence": 0.96875, "error_rate": 0.002}):
+        st1 = pb.StreamThreshold(threshold=1000, **kw)
+        assert (st1.width, st1.depth, st1.confidence, st1.error_rate, st1.elements_added) == (1000, 5, 0.96875, 0.002, 0)
+        assert st1.meets_threshold == {} and st1.threshold == 1000
+    st1 = pb.StreamThreshold(threshold=2, width=1000, depth=5)
+    assert st1.add("this is a test") == 1 and st1.meets_threshold == {}
+    assert st1.add("this is a test") == 2 and st1.meets_threshold == {"this is a test": 2}
+    assert st1.add("this is not a test") == 1 and st1.add("this is a test") == 3
+    assert st1.add("this is not a test") == 2 and st1.add("this is still not a test") == 1
+    assert st1.meets_threshold == {"this is a test": 3, "this is not a test": 2} and st1.elements_added == 6
+    st1 = pb.StreamThreshold(threshold=10, width=1000, depth=5)
+    got = st1.add_many(["this is a test", "this is a test", "this is not a test", "this is a test", "this is not a test"],
+                       np.array([5, 5, 9, 20, 2]))
+    assert got.tolist() == [5, 10, 9, 30, 11]
+    assert st1.meets_threshold == {"this is a test": 30, "this is not a test": 11} and st1.elements_added == 41
+    assert st1.remove("this is a test") == 29 and st1.meets_threshold == {"this is a test": 29, "this is not a test": 11}
+    assert st1.remove("this is not a test") == 10 and st1.remove("this is not a test") == 9
+    assert st1.meets_threshold == {"this is a test": 29} and st1.elements_added == 38
+    st1 = pb.StreamThreshold(threshold=10, width=1000, depth=5)
+    assert st1.add("this is a test", 30) == 30 and st1.add("this is not a test", 11) == 11 and st1.elements_added == 41
+    assert st1.remove("this is not a test", 2) == 9 and st1.meets_threshold == {"this is a test": 30} and st1.elements_added == 39
+    st1.clear()
+    assert st1.meets_threshold == {} and st1.elements_added == 0
+    st1 = pb.StreamThreshold(threshold=10, width=1000, depth=5)
+    assert st1.add("this is a test", 100) == 100 and md5(bytes(st1)) == "fb1c39dd1a73f1ef0d7fc79f60fc028e"
+    path = tmp_path / "s.cms"
+    st1.export(path)
+    st2 = pb.StreamThreshold(threshold=10, filepath=path)
+    assert (st2.width, st2.depth, st2.elements_added, st2.check("this is a test"), st2.meets_threshold) == (1000, 5, 100, 100, {})
+    assert st2.add("this is a test", 1) == 101 and st2.meets_threshold == {"this is a test": 101}
+    st3 = pb.StreamThreshold.frombytes(bytes(st1), threshold=10)
+    assert (st3.threshold, st3.elements_added, st3.check("this is a test")) == (10, 100, 100) and bytes(st3) == bytes(st1)
+    assert str(st1) == ("Stream Threshold Count-Min Sketch:\n\tWidth: 1000\n\tDepth: 5\n\tConfidence: 0.96875\n\tError Rate: 0.002\n"
+                        "\tElements Added: 100\n\tThreshold: 10\n\tNumber Meeting Threshold: 1")
+    with pytest.raises(pb.NotSupportedError):
+        st1.join(pb.StreamThreshold(threshold=1000, width=1000, depth=5))
+
+
+def test_expanding_rotating_reference_test_file_io(pb, tmp_path):
+    # tests/expandingbloom_test.py:111-160
+    blm = pb.ExpandingBloomFilter(est_elements=25, false_positive_rate=0.05)
+    blm.add_many([str(i) for i in range(105)])
+    blm2 = pb.ExpandingBloomFilter.frombytes(bytes(blm))
+    assert (blm2.expansions, blm2.false_positive_rate, blm2.estimated_elements, blm2.elements_added) == (3, 0.05000000074505806, 25, 105)
+    assert bytes(blm2) == bytes(blm) and blm.check_many([str(i) for i in range(105)]).all()
+    path = tmp_path / "e.ebf"
+    pb.ExpandingBloomFilter(est_elements=25, false_positive_rate=0.05).export(path)
+    assert md5(path.read_bytes()) == "eb5769ae9babdf7b37d6ce64d58812bc"
+    assert [b.elements_added for b in pb.ExpandingBloomFilter(filepath=path)._blooms] == [0]
+    blm = pb.ExpandingBloomFilter(est_elements=25, false_positive_rate=0.05)
+    for i in range(15):
+        blm.add(f"{i}")
+        blm.push()
+    blm.export(path)
+    blm2 = pb.ExpandingBloomFilter(filepath=path)
+    assert blm2.expansions == 15 and all(f"{i}" in blm2 for i in range(15)) and not any(f"{i}" in blm2 for i in range(99, 125))
+    # :266-318
+    rbf = pb.RotatingBloomFilter(est_elements=25, false_positive_rate=0.05, max_queue_size=3)
+    rbf.add_many([str(i) for i in range(105)])
+    rbf2 = pb.RotatingBloomFilter.frombytes(bytes(rbf), max_queue_size=3)
+    assert (rbf2.expansions, rbf2.false_positive_rate, rbf2.estimated_elements, rbf2.elements_added) == (2, 0.05000000074505806, 25, 105)
+    assert rbf2.current_queue_size == 3 and bytes(rbf2) == bytes(rbf)
+    keys = [str(i) for i in range(105)]
+    assert (rbf.check_many(keys) == rbf2.check_many(keys)).all()
+    rpath = tmp_path / "r.rbf"
+    pb.RotatingBloomFilter(est_elements=25, false_positive_rate=0.05).export(rpath)
+    assert md5(rpath.read_bytes()) == "eb5769ae9babdf7b37d6ce64d58812bc"
+    rbf = pb.RotatingBloomFilter(est_elements=25, false_positive_rate=0.05)
+    for i in range(15):
+        rbf.add(f"{i}")
+        rbf.push()
+    rbf.export(rpath)
+    rbf2 = pb.RotatingBloomFilter(filepath=rpath)
+    assert not any(f"{i}" in rbf2 for i in range(5)) and all(f"{i}" in rbf2 for i in range(6, 15))
+    assert (rbf2.current_queue_size, rbf2.expansions, rbf2.elements_added) == (10, 9, 15)
