@@ -185,7 +185,7 @@ int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, 
  * (pb_bloom_index_keys, or plugin hashes reduced mod num_bits), all on the device.
  * pb_bloom_novel_rows: novel_dev[i] = 1 iff adding the rows one at a time, in order, would add row i to this filter
  *   (rows with skip_dev[i] != 0 -- found in an older filter -- take no part; skip_dev may be NULL).  Read-only on the
- *   bits; keeps a 4-byte-per-bit table on the handle until pb_bloom_release_scratch.
+ *   bits; at most 2^24 rows per call; keeps a 4-byte-per-bit table on the handle until pb_bloom_release_scratch.
  * pb_bloom_add_rows: bloom.py:241-250 for the rows with mask_dev[i] != 0 (NULL: all rows). */
 int pb_bloom_novel_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *skip_dev, uint8_t *novel_dev);
 int pb_bloom_add_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *mask_dev);

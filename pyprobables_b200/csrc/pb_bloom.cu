@@ -34,7 +34,8 @@ struct pb_bloom {
     uint64_t nbytes = 0;  // ceil((hi-lo)/8)
     uint64_t nwords = 0;  // allocation, multiple of 4 words
     FastMod fm;
-    uint32_t *first_setter = nullptr;  // check-then-add batches: per owned bit, lowest row that would set it (all ~0u between calls)
+    uint32_t *first_setter = nullptr;  // check-then-add batches: per owned bit, (0xFF - epoch) << 24 | lowest row of the call that touched it
+    uint32_t first_epoch = 0;          // 1..254; a later call's tags are smaller than any earlier call's, so stale entries lose the min
 };
 
 namespace pb {
@@ -186,35 +187,33 @@ __global__ void __launch_bounds__(256)
 // that are found add nothing new (all their bits are set already), so the bits set before key i's turn are the
 // filter's bits plus the bits of ALL earlier rows that are not skipped, and key i is added iff it owns a bit that is
 // clear in the filter and that no earlier row touches: first_setter[bit] = min row over the batch, then one compare.
+// The table is never reset between calls: entries carry the call's epoch in their top byte, counted DOWN, so whatever
+// an earlier call left behind is larger than anything this call writes and loses the atomicMin.
 __global__ void __launch_bounds__(256)
     bloom_first_setter_kernel(const uint64_t *__restrict__ idx, uint64_t n_entries, uint32_t k, BloomDev b,
-                              const uint8_t *__restrict__ skip, uint32_t *__restrict__ first) {
+                              const uint8_t *__restrict__ skip, uint32_t *__restrict__ first, uint32_t tag) {
     for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t row = e / k;
         if (skip && skip[row]) continue;
         const uint64_t l = __ldcs(idx + e) - b.lo;
-        if (!((__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u)) atomicMin(first + l, (uint32_t)row);
+        if (!((__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u)) atomicMin(first + l, tag | (uint32_t)row);
     }
 }
 __global__ void __launch_bounds__(256)
     bloom_novel_rows_kernel(const uint64_t *__restrict__ idx, uint64_t n, uint32_t k, BloomDev b,
-                            const uint8_t *__restrict__ skip, const uint32_t *__restrict__ first, uint8_t *__restrict__ novel) {
+                            const uint8_t *__restrict__ skip, const uint32_t *__restrict__ first, uint32_t tag,
+                            uint8_t *__restrict__ novel) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t nv = 0;
         if (!(skip && skip[i])) {
             for (uint32_t s = 0; s < k; ++s) {
                 const uint64_t l = idx[i * k + s] - b.lo;
                 const bool clear = !((__ldg(b.words + (l >> 5)) >> (uint32_t)(l & 31)) & 1u);
-                nv |= (clear && __ldcg(first + l) == (uint32_t)i) ? 1u : 0u;
+                nv |= (clear && __ldcg(first + l) == (tag | (uint32_t)i)) ? 1u : 0u;
             }
         }
         novel[i] = (uint8_t)nv;
     }
-}
-__global__ void __launch_bounds__(256)
-    bloom_first_setter_reset_kernel(const uint64_t *__restrict__ idx, uint64_t n_entries, BloomDev b, uint32_t *__restrict__ first) {
-    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x)
-        first[__ldcs(idx + e) - b.lo] = 0xFFFFFFFFu;
 }
 // rows [0, n) of k bit indices each; a row is applied iff mask[row] != 0 (mask NULL: every row)
 __global__ void __launch_bounds__(256)
@@ -1046,27 +1045,29 @@ static int rows_in_range(pb_bloom *b, const uint64_t *idx_dev, uint64_t n_entrie
 // older filter of the stack).  The filter itself is not modified.
 int pb_bloom_novel_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *skip_dev, uint8_t *novel_dev) {
     PB_REQUIRE(b && ((idx_dev && novel_dev) || n == 0), "NULL argument");
-    PB_REQUIRE(n < 0xFFFFFFFFull, "at most 2^32 - 2 rows per call");
+    PB_REQUIRE(n <= (1ull << 24), "at most 2^24 rows per call (24-bit row numbers in the first-setter table)");
     if (n == 0) return PB_OK;
     pb_ctx *ctx = b->ctx;
     DeviceGuard g(ctx->device);
     const uint64_t n_entries = n * b->k;
     PB_TRY(rows_in_range(b, idx_dev, n_entries));
+    const size_t table_bytes = b->nwords * 32 * sizeof(uint32_t);
     if (!b->first_setter) {
-        PB_CUDA(cudaMalloc(&b->first_setter, b->nwords * 32 * sizeof(uint32_t)));
-        PB_CUDA(cudaMemsetAsync(b->first_setter, 0xFF, b->nwords * 32 * sizeof(uint32_t), ctx->stream));
+        PB_CUDA(cudaMalloc(&b->first_setter, table_bytes));
+        b->first_epoch = 0;
     }
+    if (b->first_epoch == 0 || b->first_epoch >= 254) {  // fresh table, or the epochs have run out: start over
+        PB_CUDA(cudaMemsetAsync(b->first_setter, 0xFF, table_bytes, ctx->stream));
+        b->first_epoch = 0;
+    }
+    const uint32_t tag = (0xFFu - ++b->first_epoch) << 24;
     const BloomDev bd = dev_view(b);
-    const int ge = grid_for(ctx, n_entries, 256, 8);
     launch_begin(ctx);
-    bloom_first_setter_kernel<<<ge, 256, 0, ctx->stream>>>(idx_dev, n_entries, b->k, bd, skip_dev, b->first_setter);
+    bloom_first_setter_kernel<<<grid_for(ctx, n_entries, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n_entries, b->k, bd, skip_dev, b->first_setter, tag);
     PB_TRY(check_launch(ctx, "bloom_first_setter"));
     launch_begin(ctx);
-    bloom_novel_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, b->k, bd, skip_dev, b->first_setter, novel_dev);
-    PB_TRY(check_launch(ctx, "bloom_novel_rows"));
-    launch_begin(ctx);
-    bloom_first_setter_reset_kernel<<<ge, 256, 0, ctx->stream>>>(idx_dev, n_entries, bd, b->first_setter);
-    return check_launch(ctx, "bloom_first_setter_reset");
+    bloom_novel_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(idx_dev, n, b->k, bd, skip_dev, b->first_setter, tag, novel_dev);
+    return check_launch(ctx, "bloom_novel_rows");
 }
 
 // BloomFilter.add_alt (bloom.py:241-250) for the rows whose mask byte is non-zero (NULL: all rows); the caller keeps

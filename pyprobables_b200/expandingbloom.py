@@ -204,10 +204,13 @@ class ExpandingBloomFilter:
         pos = 0
         with torch.cuda.stream(stream):
             while pos < n:
-                rows = idx[pos : pos + _CHUNK_ROWS]
-                cnt = rows.shape[0]
                 newest = self._blooms[-1]
                 room = self._room()
+                # no more than `room` rows of a slice can be applied before the stack has to grow, and the rows after
+                # that point are taken up again anyway: size the slice to the room (plus the few rows that get skipped)
+                take_rows = _CHUNK_ROWS if not room else min(_CHUNK_ROWS, room + room // 4 + 4096)
+                rows = idx[pos : pos + take_rows]
+                cnt = rows.shape[0]
                 if force:
                     if room == 0:  # :168 -- the next key grows the stack whatever it is
                         self._grow()
