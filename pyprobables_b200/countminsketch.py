@@ -27,7 +27,7 @@ from . import _native
 from ._limits import INT64_T_MAX, INT64_T_MIN
 from .exceptions import CountMinSketchError, InitializationError, NotSupportedError
 from .hashes import default_fnv_1a, is_default_hash
-from .keys import device_batch, pack_keys
+from .keys import device_batch, pack_keys, slice_batch
 
 _FOOTER = struct.Struct("IIq")  # width, depth, elements_added (countminsketch.py:122)
 _U64_MASK = (1 << 64) - 1
@@ -272,21 +272,22 @@ class CountMinSketch:
             if n == 0:
                 return out
             table = device_view(self.device_ptr(), d * w, "<i4", self._ctx.device)
-            if self._fused:
-                idx = torch.empty((n, d), dtype=torch.int64, device=dev)
-                _native.call("pb_bloom_index_keys", self._ctx.handle, dkb.ref(), w, d, C.c_void_p(idx.data_ptr()))
-            else:
-                idx = torch.from_numpy((h % np.uint64(w)).view(np.int64)).to(dev)
             amounts = None if scalar else torch.from_numpy(num_els).to(dev)
             ea = max(INT64_T_MIN, min(INT64_T_MAX, self._elements_added))
             for lo in range(0, n, _RETURNS_CHUNK):
                 hi = min(lo + _RETURNS_CHUNK, n)
                 cn = hi - lo
+                # counter columns of this chunk's keys (rows of d indices; the scratch stays at chunk size)
+                if self._fused:
+                    rows = torch.empty((cn, d), dtype=torch.int64, device=dev)
+                    _native.call("pb_bloom_index_keys", self._ctx.handle, slice_batch(dkb, lo, hi).ref(), w, d, C.c_void_p(rows.data_ptr()))
+                else:
+                    rows = torch.from_numpy((h[lo:hi] % np.uint64(w)).view(np.int64)).to(dev)
                 wv = torch.full((cn,), int(num_els), dtype=torch.int64, device=dev) if scalar else amounts[lo:hi]
                 ar = torch.arange(cn, device=dev)
                 vals = torch.empty((cn, d), dtype=torch.int64, device=dev)
                 for r in range(d):
-                    cs, order = torch.sort(idx[lo:hi, r], stable=True)
+                    cs, order = torch.sort(rows[:, r].contiguous(), stable=True)
                     ws = wv[order]
                     csum = torch.cumsum(ws, 0)
                     start = torch.ones(cn, dtype=torch.bool, device=dev)
@@ -295,7 +296,6 @@ class CountMinSketch:
                     run = csum - (csum - ws)[first]  # amounts on this counter up to and including each key
                     vals[order, r] = torch.clamp(table[r * w + cs].to(torch.int64) + run, max=INT32_T_MAX)
                 # the table itself moves through the add kernel (same end state as add_many, saturation included)
-                rows = idx[lo:hi]
                 ea_c = C.c_int64(0)
                 _native.call("pb_cms_add_hashes", self._h, C.c_void_p(rows.data_ptr()), cn, 1,
                              None if scalar else C.c_void_p(wv.data_ptr()), int(num_els) if scalar else 0, C.byref(ea_c))

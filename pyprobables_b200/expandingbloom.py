@@ -33,11 +33,12 @@ from . import _native
 from .bloom import BloomFilter, _is_file
 from .exceptions import RotatingBloomFilterError
 from .hashes import default_fnv_1a, is_default_hash
-from .keys import device_batch, pack_keys
+from .keys import device_batch, pack_keys, slice_batch
 
 _FOOTER = struct.Struct("QQQf")  # expandingbloom.py:72
 _U64 = struct.Struct("Q")  # :73
-_CHUNK_ROWS = 1 << 24  # rows taken up at once: bounds the scratch (rows x k x 8 bytes) whatever the batch size
+_CHUNK_ROWS = 1 << 24  # rows of one pb_bloom_novel_rows call (24-bit row numbers in its table)
+_BLOCK_KEYS = 1 << 27  # keys hashed to rows of bit indices at once: bounds the scratch (keys x k x 8 bytes) whatever the batch size
 
 
 class ExpandingBloomFilter:
@@ -127,8 +128,9 @@ class ExpandingBloomFilter:
 
         return torch, torch.cuda.ExternalStream(self._ctx.stream, device=f"cuda:{self._ctx.device}")
 
-    def _rows(self, keys):
-        """-> (int64 CUDA tensor [n, k] holding the u64 bit indices, n, keys_were_on_device)"""
+    def _row_blocks(self, keys, block_keys: int = _BLOCK_KEYS):
+        """the batch in key order as blocks of at most `block_keys` rows of bit indices (bounds the scratch at
+        block_keys x k x 8 bytes whatever the batch size); yields (idx, n_rows, keys_were_on_device)"""
         torch, stream = self._torch()
         first = self._blooms[0]
         k, m = first.number_hashes, first.number_bits
@@ -136,17 +138,22 @@ class ExpandingBloomFilter:
         if self._fused:
             kb = pack_keys(keys)
             was_dev = kb.on_device
-            dkb = device_batch(kb, self._ctx.device)
-            with torch.cuda.stream(stream):
-                idx = torch.empty((kb.n, k), dtype=torch.int64, device=dev)
-                if kb.n:
-                    _native.call("pb_bloom_index_keys", self._ctx.handle, dkb.ref(), m, k, C.c_void_p(idx.data_ptr()))
-                    self._ctx.synchronize()  # dkb's buffers may go away with this frame
-            return idx, kb.n, was_dev
+            for lo in range(0, max(kb.n, 1), block_keys):
+                part = slice_batch(kb, lo, lo + block_keys)
+                dpart = device_batch(part, self._ctx.device)
+                with torch.cuda.stream(stream):
+                    idx = torch.empty((part.n, k), dtype=torch.int64, device=dev)
+                    if part.n:
+                        _native.call("pb_bloom_index_keys", self._ctx.handle, dpart.ref(), m, k, C.c_void_p(idx.data_ptr()))
+                        self._ctx.synchronize()  # dpart's buffers may go away with this frame
+                yield idx, part.n, was_dev
+            return
         if isinstance(keys, (str, bytes, bytearray, memoryview)):
             keys = [keys]
-        h, n = first._plugin_hashes(keys)
-        return self._rows_from_hashes(h % np.uint64(m)), n, False
+        keys = list(keys)
+        for lo in range(0, max(len(keys), 1), block_keys):
+            h, n = first._plugin_hashes(keys[lo : lo + block_keys])
+            yield self._rows_from_hashes(h % np.uint64(m)), n, False
 
     def _rows_from_hashes(self, h: np.ndarray):
         torch, stream = self._torch()
@@ -167,10 +174,12 @@ class ExpandingBloomFilter:
     def check_many(self, keys):
         """ExpandingBloomFilter.check for every key -> bool[n] (a CUDA tensor of keys gets a CUDA tensor back)"""
         torch, stream = self._torch()
-        idx, n, was_dev = self._rows(keys)
-        with torch.cuda.stream(stream):
-            found = self._found(self._blooms, idx).bool()
-            self._ctx.synchronize()
+        parts, was_dev = [], False
+        for idx, _, was_dev in self._row_blocks(keys):
+            with torch.cuda.stream(stream):
+                parts.append(self._found(self._blooms, idx).bool())
+                self._ctx.synchronize()
+        found = torch.cat(parts) if len(parts) != 1 else parts[0]
         return found if was_dev else found.cpu().numpy()
 
     def check(self, key) -> bool:
@@ -188,8 +197,8 @@ class ExpandingBloomFilter:
     def add_many(self, keys, force: bool = False) -> None:
         """ExpandingBloomFilter.add for every key of the batch, in order; the result (bitmaps, per-filter counts, number
         of filters) is the one the reference reaches adding the keys one at a time"""
-        idx, n, _ = self._rows(keys)
-        self._add_rows(idx, n, force)
+        for idx, n, _ in self._row_blocks(keys):
+            self._add_rows(idx, n, force)
 
     def add(self, key, force: bool = False) -> None:
         self.add_many([key], force)

@@ -163,14 +163,26 @@ def device_batch(kb: KeyBatch, device: int) -> KeyBatch:
 
     dev = f"cuda:{device}"
     offs = None
-    n_sym = int(kb.c.stride) * kb.n
+    sw = int(kb.c.sym_width)
+    first_sym, n_sym = 0, int(kb.c.stride) * kb.n
     if kb.c.offsets:
         o = np.frombuffer((C.c_uint64 * (kb.n + 1)).from_address(kb.c.offsets), dtype=np.uint64)
-        n_sym = int(o[-1])
-        offs = torch.from_numpy(o.astype(np.int64)).to(dev)
-    nbytes = n_sym * int(kb.c.sym_width)
-    raw = np.frombuffer((C.c_uint8 * nbytes).from_address(kb.c.data), dtype=np.uint8) if nbytes else np.zeros(0, np.uint8)
+        first_sym, n_sym = int(o[0]), int(o[-1]) - int(o[0])  # (a slice of a larger batch starts somewhere inside `data`)
+        offs = torch.from_numpy((o - o[0]).astype(np.int64)).to(dev)
+    nbytes = n_sym * sw
+    raw = (np.frombuffer((C.c_uint8 * nbytes).from_address(kb.c.data + first_sym * sw), dtype=np.uint8) if nbytes
+           else np.zeros(0, np.uint8))
     data = torch.from_numpy(np.concatenate([raw, np.zeros(16, np.uint8)])).to(dev)  # (copy + tail padding)
     torch.cuda.current_stream(data.device).synchronize()
     return KeyBatch(data.data_ptr(), offs.data_ptr() if offs is not None else None, kb.n, int(kb.c.stride), int(kb.c.sym_width),
                     True, (data, offs))
+
+
+def slice_batch(kb: KeyBatch, lo: int, hi: int) -> KeyBatch:
+    """keys [lo, hi) of a packed batch as a batch of their own (a view: same buffers, same residency)"""
+    lo, hi = max(0, lo), min(kb.n, hi)
+    sw = int(kb.c.sym_width)
+    if kb.c.offsets:  # offsets are absolute symbol positions in `data`: the window just starts later in the offsets array
+        return KeyBatch(kb.c.data, kb.c.offsets + 8 * lo, hi - lo, 0, sw, kb.on_device, kb._keep)
+    stride = int(kb.c.stride)
+    return KeyBatch((kb.c.data or 0) + lo * stride * sw, None, hi - lo, stride, sw, kb.on_device, kb._keep)
