@@ -184,8 +184,11 @@ __device__ __forceinline__ void apply_smem_init(ApplySmem &sm) {
 
 // `g` counts the tiles this CTA has pushed through the stages so far (stage = g % S, mbarrier phase = g / S & 1);
 // it is CTA-uniform and carried from list to list.  All threads of the CTA call this together.
+// ADD: the window is a slice of a COUNTER array (Counting Bloom) and every entry adds `amount` to its counter
+// instead of setting its bit.
+template <bool ADD = false>
 __device__ __forceinline__ void apply_list_tma(uint32_t *__restrict__ words, const uint32_t *__restrict__ list, uint32_t cnt, ApplySmem &sm,
-                                               uint32_t &g) {
+                                               uint32_t &g, uint32_t amount = 1u) {
     const uint32_t T = (cnt + kApplyTile - 1) / kApplyTile;
     auto issue = [&](uint32_t i) {  // thread 0 only
         const uint32_t st = (g + i) % kApplyStages;
@@ -207,10 +210,17 @@ __device__ __forceinline__ void apply_list_tma(uint32_t *__restrict__ words, con
             const uint32_t e = (q * 256 + threadIdx.x) * 4;
             if (e < n) {
                 const uint4 v = b4[q * 256 + threadIdx.x];
-                atomicOr(words + (v.x >> 5), 1u << (v.x & 31));
-                if (e + 1 < n) atomicOr(words + (v.y >> 5), 1u << (v.y & 31));
-                if (e + 2 < n) atomicOr(words + (v.z >> 5), 1u << (v.z & 31));
-                if (e + 3 < n) atomicOr(words + (v.w >> 5), 1u << (v.w & 31));
+                if (ADD) {
+                    atomicAdd(words + v.x, amount);
+                    if (e + 1 < n) atomicAdd(words + v.y, amount);
+                    if (e + 2 < n) atomicAdd(words + v.z, amount);
+                    if (e + 3 < n) atomicAdd(words + v.w, amount);
+                } else {
+                    atomicOr(words + (v.x >> 5), 1u << (v.x & 31));
+                    if (e + 1 < n) atomicOr(words + (v.y >> 5), 1u << (v.y & 31));
+                    if (e + 2 < n) atomicOr(words + (v.z >> 5), 1u << (v.z & 31));
+                    if (e + 3 < n) atomicOr(words + (v.w >> 5), 1u << (v.w & 31));
+                }
             }
         }
         __syncthreads();  // everybody is done reading the stage before it is refilled
@@ -232,6 +242,23 @@ static __global__ void __launch_bounds__(256) bloom_apply2(PartDev p, uint32_t c
         uint32_t cnt = p.counts[li];
         if (cnt > p.sub_cap) cnt = p.sub_cap;
         apply_list_tma(words, p.stage + li * p.sub_cap, cnt, sm, g);
+    }
+}
+
+// pass 2 for a Counting Bloom filter: windows of 2^window_log2 COUNTERS (p.words = the counter array); an index that
+// two hashes of one key share is listed twice and counts twice, as countingbloom.py:143-153 does
+static __global__ void __launch_bounds__(256) cbloom_apply2(PartDev p, uint32_t ctas_per_window, uint32_t amount) {
+    __shared__ ApplySmem sm;
+    apply_smem_init(sm);
+    const uint32_t w = blockIdx.x / ctas_per_window;
+    const uint32_t c = blockIdx.x % ctas_per_window;
+    uint32_t *counters = p.words + ((uint64_t)w << p.window_log2);
+    uint32_t g = 0;
+    for (uint32_t s = c; s < p.n_sub; s += ctas_per_window) {
+        const size_t li = (size_t)w * p.n_sub + s;
+        uint32_t cnt = p.counts[li];
+        if (cnt > p.sub_cap) cnt = p.sub_cap;
+        apply_list_tma<true>(counters, p.stage + li * p.sub_cap, cnt, sm, g, amount);
     }
 }
 

@@ -25,6 +25,7 @@
 #include "pb_common.cuh"
 #include "pb_hash.cuh"
 #include "pb_keys.cuh"
+#include "pb_bloom_part.cuh"
 
 using namespace pb;
 
@@ -330,6 +331,114 @@ static bool note_add(pb_cbloom *b, uint64_t n, uint64_t num) {
     return b->added_bound <= (uint64_t)kU32Max;
 }
 
+// ---- partitioned add (the Bloom insert's two passes, pb_bloom_part.cuh, on a counter array) ------------------------
+// A random RED.ADD on a DRAM-resident counter array costs a sector read-modify-write (21.7 G/s measured).  Pass 1 bins
+// the counter indices of a chunk by window of 2^wl counters (16 MB: L2 resident), pass 2 streams each window's lists and
+// adds in L2.  Only while the handle can prove that no counter reaches 2^32 (plain RED.ADD, no saturation), for k <= 16.
+__global__ void __launch_bounds__(256) cbloom_apply_overflow(const uint64_t *__restrict__ list, const unsigned long long *count, uint64_t cap,
+                                                             uint32_t *__restrict__ counters, uint32_t amount) {
+    const uint64_t n = *count < cap ? *count : cap;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(counters + list[i], amount);
+}
+
+struct CbPartPlan {
+    bool use = false;
+    uint32_t window_log2 = 0, n_windows = 0;
+    uint64_t chunk_keys = 0;
+    PartLayout lay{};
+};
+
+static CbPartPlan plan_cb_partition(const pb_cbloom *b, const pb_keys *keys, bool safe) {
+    CbPartPlan pl;
+    pb_ctx *ctx = b->ctx;
+    const int64_t mode = ctx->bloom_insert_mode;  // 0 auto, 1 direct, 2 partitioned (shared with the Bloom insert)
+    const uint64_t n = keys->n;
+    if (mode == 1 || !safe || b->k > kMaxPartK || n == 0) return pl;
+    const uint64_t bytes = b->n_counters * 4;
+    const uint64_t l2 = ctx->l2_bytes ? ctx->l2_bytes : ((uint64_t)96 << 20);
+    if (mode == 0) {
+        if (bytes <= l2) return pl;                                        // the direct REDs hit L2 anyway
+        if ((double)n * b->k * 64.0 < 4.0 * (double)bytes) return pl;      // one read+write of the array per chunk must pay
+    }
+    // the same window BYTES as the Bloom insert: 2^(bits-5) counters
+    uint32_t wl = (uint32_t)std::max<int64_t>(5, std::min<int64_t>(ctx->bloom_window_log2_bits - 5, 26));
+    while (((b->n_counters + ((1ull << wl) - 1)) >> wl) > (uint64_t)kMaxWindows2 && wl < 26) ++wl;
+    const uint64_t nw = (b->n_counters + ((1ull << wl) - 1)) >> wl;
+    if (nw > (uint64_t)kMaxWindows2) return pl;
+    const bool fixed16 = keys->offsets == nullptr && keys->sym_width == 1 && keys->stride == 16;
+    const uint64_t budget_entries = std::min<uint64_t>((uint64_t)ctx->stage_bytes / 4, 0xFFFFFFF0ull);
+    uint64_t chunk = std::min<uint64_t>(n, 1ull << 27);
+    PartLayout lay;
+    for (;;) {
+        lay = part_layout(ctx, chunk, b->k, b->n_counters, wl, (uint32_t)nw, fixed16, false);
+        if ((uint64_t)lay.sub_cap * (uint64_t)lay.grid * nw <= budget_entries) break;
+        if (chunk <= 4096) return pl;
+        chunk = chunk - chunk / 4;
+    }
+    pl.use = true;
+    pl.window_log2 = wl;
+    pl.n_windows = (uint32_t)nw;
+    pl.chunk_keys = chunk;
+    pl.lay = lay;
+    return pl;
+}
+
+struct CbPartArgs {
+    pb_cbloom *b;
+    CbPartPlan plan;
+    uint32_t num;
+};
+
+static int cb_part_chunk(pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) {
+    (void)first;
+    (void)slot;
+    CbPartArgs *a = (CbPartArgs *)user;
+    pb_cbloom *b = a->b;
+    const CbPartPlan &pl = a->plan;
+    const size_t n_lists = (size_t)pl.n_windows * (size_t)pl.lay.grid;
+    PB_TRY(scratch_reserve(ctx, ctx->part_stage, n_lists * pl.lay.sub_cap * 4));
+    PB_TRY(scratch_reserve(ctx, ctx->part_cursors, n_lists * 4));
+    PartDev pd;
+    pd.stage = (uint32_t *)ctx->part_stage.p;
+    pd.counts = (uint32_t *)ctx->part_cursors.p;
+    pd.words = b->counts;
+    part_set_modulus(pd, b->n_counters);
+    pd.sub_cap = pl.lay.sub_cap;
+    pd.n_sub = (uint32_t)pl.lay.grid;
+    pd.window_log2 = pl.window_log2;
+    pd.n_windows = pl.n_windows;
+    pd.k = b->k;
+    // indices that do not fit their sublist (7 sigma: practically never) go to a side list and are added one by one
+    constexpr uint64_t kOvfCap = 1ull << 20;
+    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[1], kOvfCap * 8));
+    PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
+    unsigned long long *ovf_count = (unsigned long long *)ctx->small.p + 48;
+    PB_CUDA(cudaMemsetAsync(ovf_count, 0, 8, ctx->stream));
+    pd.ovf_list = (uint64_t *)ctx->aux_stage[1].p;
+    pd.ovf_count = ovf_count;
+    pd.ovf_cap = kOvfCap;
+    launch_begin(ctx);
+    cudaError_t e = launch_part4(pl.lay.block, ctx->stream, dk, pd);
+    if (e != cudaSuccess) {
+        set_error("launch of bloom_part4 (counting bloom, k=%u) failed: %s", pd.k, cudaGetErrorString(e));
+        return PB_ERR_CUDA;
+    }
+    PB_TRY(check_launch(ctx, "cbloom_part"));
+    const uint32_t cpw = (uint32_t)ctx->num_sms * (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->bloom_apply_cpw_per_sm, 32));
+    launch_begin(ctx);
+    cbloom_apply2<<<pl.n_windows * cpw, 256, 0, ctx->stream>>>(pd, cpw, a->num);
+    PB_TRY(check_launch(ctx, "cbloom_apply_windows"));
+    cbloom_apply_overflow<<<64, 256, 0, ctx->stream>>>(pd.ovf_list, ovf_count, kOvfCap, b->counts, a->num);
+    PB_TRY(check_launch(ctx, "cbloom_apply_overflow"));
+    PB_CUDA(cudaMemcpyAsync(ctx->pinned_small, ovf_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t spilled = *(uint64_t *)ctx->pinned_small;
+    PB_REQUIRE(spilled <= kOvfCap, "%llu counter indices overflowed their sublists (side list holds %llu): counters are incomplete",
+               (unsigned long long)spilled, (unsigned long long)kOvfCap);
+    return PB_OK;
+}
+
 static int stage_rows(pb_ctx *ctx, const uint64_t *hashes, uint64_t count, int on_device, const uint64_t **dev) {
     if (on_device) {
         *dev = hashes;
@@ -422,7 +531,13 @@ int pb_cbloom_add_keys(pb_cbloom *b, const pb_keys *keys, uint64_t num_els) {
     PB_REQUIRE(num_els <= (uint64_t)kU32Max, "num_els must fit 32 bits");
     DeviceGuard g(b->ctx->device);
     if (num_els == 0 || keys->n == 0) return validate_keys(keys);
-    CbArgs a{b, 0, (uint32_t)num_els, note_add(b, keys->n, num_els), nullptr, nullptr, 0};
+    const bool safe = note_add(b, keys->n, num_els);
+    CbPartPlan pl = plan_cb_partition(b, keys, safe);
+    if (pl.use) {
+        CbPartArgs pa{b, pl, (uint32_t)num_els};
+        return for_each_chunk(b->ctx, keys, cb_part_chunk, &pa, pl.chunk_keys);
+    }
+    CbArgs a{b, 0, (uint32_t)num_els, safe, nullptr, nullptr, 0};
     return for_each_chunk(b->ctx, keys, cb_chunk, &a);
 }
 

@@ -141,3 +141,38 @@ def test_set_algebra_and_plugin(pb, golden):
     assert (c.bloom_numpy() == ref).all()
     assert c.check("w5") == min(ref[h % c.number_bits] for h in pb.hashes.default_md5("w5", c.number_hashes))
     assert c.remove("w5") == c.check("w5")
+
+
+@pytest.mark.parametrize("est,fpr,wl_bits", [(300_000, 0.01, 20), (200_000, 0.0001, 22), (40_000, 0.2, 16)])
+def test_partitioned_add_equals_direct_and_oracle(pb, orc, est, fpr, wl_bits):
+    """the two-pass add (indices binned by window of counters, then added while the window is L2 resident) against the
+    oracle: several windows, repeated keys (one index listed twice counts twice), amounts > 1, a skewed batch that
+    overflows its sublists into the side list, ragged keys, and the saturating fallback once a counter could overflow"""
+    ctx = pb.default_context()
+    keys = orc.uniform_keys(0, 400_000)
+    keys[::9] = keys[:len(keys[::9])]
+    skew = np.repeat(orc.uniform_keys(7, 2), 150_000, axis=0)
+    words = [f"w{i}-{'y' * (i % 11)}" for i in range(50_000)]
+    try:
+        ctx.set_option("bloom_insert_mode", 2)
+        ctx.set_option("bloom_window_log2_bits", wl_bits)  # windows of 2^(bits-5) counters
+        c = pb.CountingBloomFilter(est, fpr)
+        o = orc.CountingBloom(c.number_bits, c.number_hashes)
+        c.add_many(keys), o.add(orc.pack(keys))
+        assert (c.bloom_numpy() == o.bloom).all()
+        c.add_many(keys[:100_000], 3), o.add(orc.pack(keys[:100_000]), 3)
+        c.add_many(skew), o.add(orc.pack(skew))
+        c.add_many(words, 2), o.add(orc.pack(words), 2)
+        assert (c.bloom_numpy() == o.bloom).all() and c.elements_added == o.elements_added
+        probes = np.concatenate([keys[:5000], orc.uniform_keys(9_000_000, 5000)])
+        assert (c.check_many(probes) == o.check(orc.pack(probes))).all()
+        before = c.bloom_numpy().astype(np.uint64)
+        c.add_many(keys[:50], 2**31)  # from here on a counter could reach 2^32: the saturating direct kernel takes over
+        c.add_many(keys[:50], 2**31)
+        inc = orc.CountingBloom(c.number_bits, c.number_hashes)
+        inc.add(orc.pack(keys[:50]), 1)  # how often each counter is hit by one pass over these 50 keys
+        want = np.minimum(before + inc.bloom.astype(np.uint64) * 2**32, 2**32 - 1)  # countingbloom.py:147-149
+        assert (c.bloom_numpy() == want).all() and int(c.bloom_numpy().max()) == 2**32 - 1
+    finally:
+        ctx.set_option("bloom_insert_mode", 0)
+        ctx.set_option("bloom_window_log2_bits", 27)
