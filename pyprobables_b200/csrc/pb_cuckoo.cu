@@ -1517,52 +1517,61 @@ struct CountsArgs {
 // CountingCuckooFilter.add, the counting half: count[fp(key)] += 1 for every key (the set half is pb_cuckoo_add_keys)
 int pb_cuckoo_counts_add_keys(pb_cuckoo *c, const pb_keys *keys) {
     PB_REQUIRE(c && keys, "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
     pb_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
     if (keys->n == 0) return validate_keys(keys);
-    PB_TRY(counts_reserve(c, keys->n));
     PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
-    unsigned long long *acc = counts_scratch(ctx);
-    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
-    CountsArgs a{c, acc, nullptr, nullptr, nullptr, nullptr};
+    CountsArgs a{c, counts_scratch(ctx), nullptr, nullptr, nullptr, nullptr};
     auto fn = [](pb_ctx *ctx, const DevKeys &dk, uint64_t first, int slot, void *user) -> int {
         (void)first;
         CountsArgs *a = (CountsArgs *)user;
+        // room for the case that every key of the chunk is a new fingerprint; chunks are at most a quarter of the map,
+        // so a stream of repeats never makes the map grow with the batch size
+        PB_TRY(counts_reserve(a->c, dk.n));
+        PB_CUDA(cudaMemsetAsync(a->acc, 0, 24, ctx->stream));
         uint32_t *fps;
         PB_TRY(chunk_fps(ctx, a->c, dk, slot, &fps));
         launch_begin(ctx);
         counts_add_kernel<<<grid_for(ctx, dk.n, 256, 8), 256, 0, ctx->stream>>>(fps, nullptr, dk.n, a->c->fp_bits, counts_view(a->c), a->acc);
-        return check_launch(ctx, "cuckoo_counts_add");
+        PB_TRY(check_launch(ctx, "cuckoo_counts_add"));
+        return counts_sync_used(a->c, a->acc);
     };
-    PB_TRY(for_each_chunk(ctx, keys, fn, &a, 1ull << 28));
-    return counts_sync_used(c, acc);
+    const uint64_t chunk = std::min<uint64_t>(1ull << 28, std::max<uint64_t>(c->cnt_cap / 4, 1ull << 16));
+    return for_each_chunk(ctx, keys, fn, &a, chunk);
 }
 
 // count[fp] += amounts[i] (NULL: 1) for host or device arrays of fingerprints (plugin hash path, load)
 int pb_cuckoo_counts_add_fingerprints(pb_cuckoo *c, const uint32_t *fps, const uint32_t *amounts, uint64_t n, int on_device) {
     PB_REQUIRE(c && (fps || n == 0), "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
     if (n == 0) return PB_OK;
     pb_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
-    PB_TRY(counts_reserve(c, n));
     PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
     unsigned long long *acc = counts_scratch(ctx);
-    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
-    const uint32_t *d_fps = fps, *d_amt = amounts;
-    if (!on_device) {
-        PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 8));
-        uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
-        PB_CUDA(cudaMemcpyAsync(d, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-        d_fps = d;
-        if (amounts) {
-            PB_CUDA(cudaMemcpyAsync(d + n, amounts, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-            d_amt = d + n;
+    for (uint64_t lo = 0; lo < n;) {
+        const uint64_t cn = std::min<uint64_t>(n - lo, std::max<uint64_t>(c->cnt_cap / 4, 1ull << 16));
+        PB_TRY(counts_reserve(c, cn));
+        PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+        const uint32_t *d_fps = fps + lo, *d_amt = amounts ? amounts + lo : nullptr;
+        if (!on_device) {
+            PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], cn * 8));
+            uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
+            PB_CUDA(cudaMemcpyAsync(d, fps + lo, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d_fps = d;
+            if (amounts) {
+                PB_CUDA(cudaMemcpyAsync(d + cn, amounts + lo, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+                d_amt = d + cn;
+            }
         }
+        launch_begin(ctx);
+        counts_add_kernel<<<grid_for(ctx, cn, 256, 8), 256, 0, ctx->stream>>>(d_fps, d_amt, cn, c->fp_bits, counts_view(c), acc);
+        PB_TRY(check_launch(ctx, "cuckoo_counts_add"));
+        PB_TRY(counts_sync_used(c, acc));
+        lo += cn;
     }
-    launch_begin(ctx);
-    counts_add_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_fps, d_amt, n, c->fp_bits, counts_view(c), acc);
-    PB_TRY(check_launch(ctx, "cuckoo_counts_add"));
-    return counts_sync_used(c, acc);
+    return PB_OK;
 }
 
 // CountingCuckooFilter.check (:175-191): the stored count of every key's fingerprint, 0 when it is not stored
@@ -1613,21 +1622,27 @@ int pb_cuckoo_counts_get_fingerprints(pb_cuckoo *c, const uint32_t *fps, uint64_
 // homeless (:264-265 hands the bin back to the caller, who raises)
 int pb_cuckoo_counts_set(pb_cuckoo *c, const uint32_t *fps, const uint32_t *vals, uint64_t n) {
     PB_REQUIRE(c && (fps || n == 0), "NULL argument");
+    PB_REQUIRE(c->cnt_cap, "pb_cuckoo_counts_enable was not called on this filter");
     if (n == 0) return PB_OK;
     pb_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
-    PB_TRY(counts_reserve(c, n));
     PB_TRY(scratch_reserve(ctx, ctx->small, 4096));
     unsigned long long *acc = counts_scratch(ctx);
-    PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
-    PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], n * 8));
-    uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
-    PB_CUDA(cudaMemcpyAsync(d, fps, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (vals) PB_CUDA(cudaMemcpyAsync(d + n, vals, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    launch_begin(ctx);
-    counts_set_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d, vals ? d + n : nullptr, n, counts_view(c), acc);
-    PB_TRY(check_launch(ctx, "cuckoo_counts_set"));
-    return counts_sync_used(c, acc);
+    for (uint64_t lo = 0; lo < n;) {
+        const uint64_t cn = std::min<uint64_t>(n - lo, std::max<uint64_t>(c->cnt_cap / 4, 1ull << 16));
+        PB_TRY(counts_reserve(c, cn));
+        PB_CUDA(cudaMemsetAsync(acc, 0, 24, ctx->stream));
+        PB_TRY(scratch_reserve(ctx, ctx->aux_stage[0], cn * 8));
+        uint32_t *d = (uint32_t *)ctx->aux_stage[0].p;
+        PB_CUDA(cudaMemcpyAsync(d, fps + lo, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (vals) PB_CUDA(cudaMemcpyAsync(d + cn, vals + lo, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        launch_begin(ctx);
+        counts_set_kernel<<<grid_for(ctx, cn, 256, 8), 256, 0, ctx->stream>>>(d, vals ? d + cn : nullptr, cn, counts_view(c), acc);
+        PB_TRY(check_launch(ctx, "cuckoo_counts_set"));
+        PB_TRY(counts_sync_used(c, acc));
+        lo += cn;
+    }
+    return PB_OK;
 }
 
 static int counts_remove_device(pb_cuckoo *c, const uint32_t *fps, const uint64_t *i2, uint64_t n, uint32_t *tickets, uint8_t *out,

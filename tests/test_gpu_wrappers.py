@@ -596,3 +596,19 @@ def test_expanding_rotating_reference_test_file_io(pb, tmp_path):
     rbf2 = pb.RotatingBloomFilter(filepath=rpath)
     assert not any(f"{i}" in rbf2 for i in range(5)) and all(f"{i}" in rbf2 for i in range(6, 15))
     assert (rbf2.current_queue_size, rbf2.expansions, rbf2.elements_added) == (10, 9, 15)
+
+
+def test_counting_cuckoo_many_repeats_small_table(pb, orc):
+    """a long stream of repeats into a small table: the count map is reserved chunk by chunk (a quarter of the map at a
+    time), never by the size of the batch"""
+    rng = np.random.default_rng(9)
+    pool = orc.uniform_keys(123, 150)
+    stream = pool[rng.integers(0, 150, 1_500_000)]
+    f = pb.CountingCuckooFilter(capacity=64, bucket_size=4, max_swaps=100, auto_expand=False)
+    f.add_many(stream)
+    counts = f.check_many(pool)
+    uniq, freq = np.unique(stream.view(np.dtype((np.void, 16))).ravel(), return_counts=True)
+    by_key = {bytes(u): int(c) for u, c in zip(uniq, freq)}
+    assert [int(c) for c in counts] == [by_key.get(k.tobytes(), 0) for k in pool]
+    assert f.elements_added == 1_500_000 and f.unique_elements == len(by_key) == 150
+    assert f.remove_many(stream[:1000]).all() and f.elements_added == 1_499_000
