@@ -180,7 +180,8 @@ def device_batch(kb: KeyBatch, device: int) -> KeyBatch:
 
 def slice_batch(kb: KeyBatch, lo: int, hi: int) -> KeyBatch:
     """keys [lo, hi) of a packed batch as a batch of their own (a view: same buffers, same residency)"""
-    lo, hi = max(0, lo), min(kb.n, hi)
+    lo = min(max(0, lo), kb.n)
+    hi = max(lo, min(kb.n, hi))
     sw = int(kb.c.sym_width)
     if kb.c.offsets:  # offsets are absolute symbol positions in `data`: the window just starts later in the offsets array
         return KeyBatch(kb.c.data, kb.c.offsets + 8 * lo, hi - lo, 0, sw, kb.on_device, kb._keep)

@@ -235,3 +235,35 @@ def test_shard_plan_is_window_aligned():
         for r in range(g):
             lo, hi = p.bounds(r)
             assert lo % (1 << p.window_log2) == 0 or lo == m
+
+
+def test_slice_batch_views_the_same_keys():
+    """keys.slice_batch (block-wise hashing in the stateful wrappers): a slice of a packed batch is the same keys, for
+    the fixed-stride and the offsets layout, u8 and u32 symbols"""
+    import ctypes as C
+
+    from pyprobables_b200.keys import pack_keys, slice_batch
+
+    def unpack(kb):
+        sw = int(kb.c.sym_width)
+        out = []
+        if kb.c.offsets:
+            o = np.frombuffer((C.c_uint64 * (kb.n + 1)).from_address(kb.c.offsets), dtype=np.uint64)
+            for a, b in zip(o[:-1], o[1:]):
+                out.append(bytes((C.c_uint8 * (int(b - a) * sw)).from_address(kb.c.data + int(a) * sw)) if b > a else b"")
+        else:
+            step = int(kb.c.stride) * sw
+            for i in range(kb.n):
+                out.append(bytes((C.c_uint8 * step).from_address(kb.c.data + i * step)))
+        return out
+
+    ragged = [f"key-{i}-{'z' * (i % 7)}" for i in range(100)]
+    fixed = np.arange(100 * 16, dtype=np.uint8).reshape(100, 16)
+    wide = [f"clé-{i}-中" for i in range(50)]
+    for batch in (ragged, fixed, wide):
+        kb = pack_keys(batch)
+        whole = unpack(kb)
+        for lo, hi in ((0, 100), (10, 35), (99, 100), (40, 40), (60, 1000)):
+            part = slice_batch(kb, lo, hi)
+            assert part.n == max(0, min(hi, kb.n) - min(lo, kb.n)) and unpack(part) == whole[lo:hi]
+            assert part.on_device == kb.on_device and int(part.c.sym_width) == int(kb.c.sym_width)
