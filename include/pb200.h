@@ -190,6 +190,8 @@ int pb_bloom_test_bit_indices(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, 
 int pb_bloom_novel_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *skip_dev, uint8_t *novel_dev);
 int pb_bloom_add_rows(pb_bloom *b, const uint64_t *idx_dev, uint64_t n, const uint8_t *mask_dev);
 int pb_bloom_release_scratch(pb_bloom *b);
+/* the table of pb_bloom_novel_rows moves on to the next filter of the stack (same geometry) instead of being freed */
+int pb_bloom_move_scratch(pb_bloom *from, pb_bloom *to);
 /* ExpandingBloomFilter.check_alt (:140-147): found_dev[i] = 1 iff one of the filters holds every bit of row i */
 int pb_bloom_rows_in_any(pb_bloom *const *filters, uint32_t n_filters, const uint64_t *idx_dev, uint64_t n, uint8_t *found_dev);
 

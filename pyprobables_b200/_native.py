@@ -127,6 +127,7 @@ SIGNATURES: dict[str, list] = {
     "pb_bloom_novel_rows": [_vp, _vp, _u64, _vp, _vp],
     "pb_bloom_add_rows": [_vp, _vp, _u64, _vp],
     "pb_bloom_release_scratch": [_vp],
+    "pb_bloom_move_scratch": [_vp, _vp],
     "pb_bloom_rows_in_any": [_vp, _u32, _vp, _u64, _vp],
     "pb_cbloom_create": [_vp, _u64, _u32, _P(_vp)],
     "pb_cbloom_destroy": [_vp],

@@ -107,9 +107,10 @@ class ExpandingBloomFilter:
 
     def _add_bloom_filter(self) -> None:
         """:171-178"""
-        if self._blooms:
-            _native.call("pb_bloom_release_scratch", self._blooms[-1]._h)
-        self._blooms.append(self._new_bloom())
+        blm = self._new_bloom()
+        if self._blooms:  # the first-setter table of the batch kernels goes with the newest filter
+            _native.call("pb_bloom_move_scratch", self._blooms[-1]._h, blm._h)
+        self._blooms.append(blm)
 
     def _newest_is_full(self) -> bool:
         """:180-183"""
@@ -337,10 +338,17 @@ class RotatingBloomFilter(ExpandingBloomFilter):
         return self._est_elements - newest.elements_added
 
     def _grow(self) -> None:
-        """:347-361 (the automatic branches)"""
+        """:347-361 (the automatic branches).  A full queue drops its oldest filter and appends an empty one of the same
+        geometry: the dropped filter's device memory is cleared and becomes the new one (no cudaFree / cudaMalloc per
+        rotation -- allocation calls, not GPU time, were what a long batch of rotations cost)."""
         if self.current_queue_size >= self._queue_size:
-            self._blooms.pop(0).close()
-        self._add_bloom_filter()
+            blm = self._blooms.pop(0)
+            blm.clear()
+            if self._blooms:
+                _native.call("pb_bloom_move_scratch", self._blooms[-1]._h, blm._h)
+            self._blooms.append(blm)
+        else:
+            self._add_bloom_filter()
 
     def pop(self) -> None:
         """:332-341"""
