@@ -1502,7 +1502,7 @@ static int counts_sync_used(pb_cuckoo *c, unsigned long long *acc) {
 int pb_cuckoo_counts_enable(pb_cuckoo *c) {
     PB_REQUIRE(c, "handle is NULL");
     DeviceGuard g(c->ctx->device);
-    const uint64_t want = counts_cap_for(c->nslots + 1);
+    const uint64_t want = counts_cap_for(c->nslots);  // (fingerprint 0 has its own entry past the hashed ones)
     if (c->cnt_cap >= want) return PB_OK;
     return counts_rebuild(c, want);
 }
