@@ -4,6 +4,7 @@
 import hashlib
 
 import numpy as np
+import pytest
 
 
 def md5(b) -> str:
@@ -83,3 +84,54 @@ def test_heavy_hitters_and_stream_threshold_vs_reference(orc, golden):
     o = orc.StreamThreshold(t["threshold"], t["width"], t["depth"])
     rets = o.add_tracked(names, orc.pack(names))
     assert md5(struct.pack(f"<{len(rets)}q", *rets.tolist())) == t["returns_md5"] and o.meets == t["meets_threshold"]
+
+
+def _bare_heavy_hitters(num_hitters):
+    """a HeavyHitters object without its device sketch: only the dictionary bookkeeping is exercised (CPU)"""
+    from pyprobables_b200.countminsketch import HeavyHitters
+
+    hh = object.__new__(HeavyHitters)
+    hh._top_x, hh._top_x_size, hh._num_hitters, hh._smallest = {}, 0, num_hitters, 0
+    return hh
+
+
+def test_heavy_hitters_bookkeeping_replays_the_reference(orc, golden):
+    """countminsketch.py:644-660 through HeavyHitters._track, fed with the reference's own return values"""
+    h = golden["heavy_hitters"]
+    names = [bytes(k).hex() for k in orc.rank_keys(np.array(h["ranks"], dtype=np.uint64))]
+    o = orc.HeavyHitters(h["num_hitters"], h["width"], h["depth"])
+    rets = o.add_tracked(names, orc.pack(names))
+    hh = _bare_heavy_hitters(h["num_hitters"])
+    for key, res in zip(names, rets.tolist()):
+        hh._track(key, res)
+    assert hh.heavy_hitters == h["heavy_hitters"] and list(hh.heavy_hitters) == list(o.top_x)  # same insertion order too
+
+
+@pytest.mark.parametrize("seed,num_hitters,n_keys,zipf", [(1, 5, 40, 1.3), (2, 20, 500, 1.1), (3, 1, 10, 2.0), (4, 50, 60, 1.05), (5, 8, 3000, 1.2)])
+def test_heavy_hitters_bulk_replay_equals_one_by_one(seed, num_hitters, n_keys, zipf):
+    """HeavyHitters._replay_rows (tracked keys updated in bulk between the pairs that change WHICH keys are tracked)
+    against _track pair by pair, on random streams whose per-key values rise like a sketch's return values do; several
+    runs back to back so that the dictionary, its stale `smallest` and the candidate filter carry over"""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    pool = rng.integers(0, 256, (n_keys, 12), dtype=np.uint8)
+    counts = np.zeros(n_keys, dtype=np.int64)
+    bulk, single = _bare_heavy_hitters(num_hitters), _bare_heavy_hitters(num_hitters)
+    for run in range(6):
+        m = int(rng.integers(1, 20_000))
+        ids = np.minimum(rng.zipf(zipf, m) - 1, n_keys - 1)
+        vals = np.empty(m, dtype=np.int64)
+        noise = rng.integers(0, 3, m)  # collisions only ever add to an estimate
+        for j, i in enumerate(ids):
+            counts[i] += 1
+            vals[j] = counts[i] + noise[j] * (counts[i] > 3)
+            counts[i] = vals[j]  # keep each key's values non-decreasing, as add()'s return values are
+        keep = vals >= bulk._smallest  # the candidate filter add_many applies per slice
+        rows, v = pool[ids[keep]], vals[keep]
+        if rows.shape[0]:
+            bulk._replay_rows(torch.from_numpy(rows), torch.from_numpy(v))
+        for i, x in zip(ids.tolist(), vals.tolist()):
+            single._track(pool[i].tobytes(), x)
+        assert bulk.heavy_hitters == single.heavy_hitters and list(bulk.heavy_hitters) == list(single.heavy_hitters)
+        assert (bulk._smallest, bulk._top_x_size) == (single._smallest, single._top_x_size)
