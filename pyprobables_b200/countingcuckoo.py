@@ -24,6 +24,22 @@ from .keys import pack_keys
 _BIN = struct.Struct("II")  # countingcuckoo.py:64
 
 
+def _first_occurrences_win(flags: np.ndarray, fps: np.ndarray) -> np.ndarray:
+    """The device hands out as many successful removals per fingerprint as its count allows, to whichever occurrences drew
+    the low tickets; one key at a time it is the FIRST occurrences that succeed (countingcuckoo.py:199-208).  Same number
+    of successes per fingerprint, moved to its earliest occurrences."""
+    order = np.argsort(fps, kind="stable")
+    sorted_fps = fps[order]
+    new_group = np.r_[True, sorted_fps[1:] != sorted_fps[:-1]]
+    starts = np.flatnonzero(new_group)
+    group = np.cumsum(new_group) - 1
+    rank = np.arange(flags.size) - starts[group]  # occurrence number of each key within its fingerprint
+    wins = np.add.reduceat(flags[order].astype(np.int64), starts)  # removals that succeeded per fingerprint
+    ordered = np.zeros_like(flags)
+    ordered[order] = rank < wins[group]
+    return ordered
+
+
 class CountingCuckooBin:
     """countingcuckoo.py:337-381 (a read-only view: the state lives on the device)"""
 
@@ -187,15 +203,7 @@ class CountingCuckooFilter(CuckooFilter):
         if 1 < res.size <= (1 << 20) and res.any() and not res.all():
             if fps is None:
                 fps = self.fingerprint_info_many(keys)[2]
-            order = np.argsort(fps, kind="stable")
-            sorted_fps = fps[order]
-            starts = np.flatnonzero(np.r_[True, sorted_fps[1:] != sorted_fps[:-1]])
-            group = np.cumsum(np.r_[True, sorted_fps[1:] != sorted_fps[:-1]]) - 1
-            rank = np.arange(res.size) - starts[group]  # occurrence number of each key within its fingerprint
-            wins = np.add.reduceat(res[order].astype(np.int64), starts)  # removals that succeeded per fingerprint
-            ordered = np.zeros_like(res)
-            ordered[order] = rank < wins[group]
-            res = ordered
+            res = _first_occurrences_win(res, fps)
         return res
 
     def remove(self, key) -> bool:

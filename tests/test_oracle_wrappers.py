@@ -135,3 +135,25 @@ def test_heavy_hitters_bulk_replay_equals_one_by_one(seed, num_hitters, n_keys, 
             single._track(pool[i].tobytes(), x)
         assert bulk.heavy_hitters == single.heavy_hitters and list(bulk.heavy_hitters) == list(single.heavy_hitters)
         assert (bulk._smallest, bulk._top_x_size) == (single._smallest, single._top_x_size)
+
+
+def test_counting_cuckoo_removal_flags_go_to_the_first_occurrences():
+    """countingcuckoo._first_occurrences_win: whatever occurrences the device let succeed, the flags end up where the
+    one-key-at-a-time loop puts them -- on the first `count` occurrences of each fingerprint"""
+    from pyprobables_b200.countingcuckoo import _first_occurrences_win
+
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        n = int(rng.integers(2, 400))
+        fps = rng.integers(1, 12, n).astype(np.uint32)
+        stored = {int(f): int(rng.integers(0, 6)) for f in np.unique(fps)}  # count of each fingerprint before the batch
+        left, sequential = dict(stored), np.zeros(n, dtype=bool)
+        for i, f in enumerate(fps.tolist()):  # the reference's loop
+            if left[f] > 0:
+                left[f] -= 1
+                sequential[i] = True
+        device = np.zeros(n, dtype=bool)  # the same number of successes per fingerprint on arbitrary occurrences
+        for f, c in stored.items():
+            where = np.flatnonzero(fps == f)
+            device[rng.permutation(where)[: min(c, where.size)]] = True
+        assert (_first_occurrences_win(device, fps) == sequential).all()
